@@ -1,0 +1,764 @@
+// libb200rank.so -- host side of the B200 score + top-K engine behind the C ABI of include/b200_rank.h.
+//
+// Reference seams (RecTools 0.17.0): `ImplicitRanker.rank` (rectools/models/rank/rank_implicit.py:187-280),
+// `ImplicitRanker._rank_on_gpu` (:148-185) and `TorchRanker.rank` (rectools/models/rank/rank_torch.py:77-177).
+// The engine keeps the object factors resident (the reference re-uploads them per call, rank_implicit.py:156),
+// stages one call's subjects / CSR filter / whitelist, runs the tensor-core candidate pass + fp64 re-score (or the
+// exhaustive fp64 kernel) and returns padded [n_rows, k] arrays plus per-row counts.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_rank.h"
+#include "common.cuh"
+#include "prep.cuh"
+#include "select.cuh"
+#include "tc_topk.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+struct CudaError {
+    cudaError_t e;
+    const char* what;
+    int line;
+};
+
+#define CK(call)                                               \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) throw CudaError{e__, #call, __LINE__}; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(sym);
+    return fn;
+}
+
+// Row-major [rows, d_pad] 16-bit matrix, boxes of [128 rows x 64 cols] (128-byte rows, SWIZZLE_128B).
+bool make_tensor_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, bool is_bf16) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)b200::tc::KBLK, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct b200_rank_engine {
+    std::mutex mu;
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    char dev_name[128] = {0};
+    int distance = B200_DIST_DOT;
+    int tc_dtype = B200_TC_FP16;  // resolved; B200_TC_OFF when the tensor-core path is unavailable
+    int64_t n_obj = 0;
+    int d = 0, d_pad = 0;
+    int64_t n_obj_pad = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {nullptr};
+
+    // resident object data
+    DevBuf obj32;     // [n_obj, d] fp32 master copy
+    DevBuf obj16;     // [n_obj_pad, d_pad] fp16 / bf16, pre-scaled (and pre-normalised for COSINE)
+    DevBuf obj_norms; // [n_obj] fp32 (COSINE)
+    int obj_exp = 0;
+    int64_t id_offset = 0;
+    float max_obj_norm = 0.f;
+    bool obj32_owned = true;
+    const float* obj32_ptr = nullptr;
+    CUtensorMap tm_obj_full;
+    bool tm_obj_ok = false;
+
+    // resident subjects (optional)
+    DevBuf sub32_res;
+    int64_t n_sub_res = 0;
+    const float* sub32_res_ptr = nullptr;
+
+    // per-call staging / workspace
+    DevBuf sub32, sub16, row_exp, rowmap, indptr, indices, wl, obj16_wl;
+    DevBuf out_ids, out_scores, out_counts;
+    DevBuf cand_scores, cand_ids, cand_counts;
+    DevBuf part_scores, part_ids;
+    DevBuf fb_rows, scratch;
+    int32_t* h_pinned = nullptr;  // small pinned scratch (fallback count)
+
+    size_t hbm_bytes() const {
+        const DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
+                               &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
+                               &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch};
+        size_t t = 0;
+        for (auto* b : all) t += b->cap;
+        return t;
+    }
+    void free_all() {
+        DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
+                         &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
+                         &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch};
+        for (auto* b : all) b->release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+        st = nullptr;
+    }
+};
+
+namespace {
+
+using namespace b200;
+
+int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// ---- resident objects -------------------------------------------------------------------------------------
+void prepare_objects(b200_rank_engine* E, int tc_mode) {
+    const int64_t n = E->n_obj;
+    const int d = E->d;
+    E->scratch.ensure(64);
+    unsigned* g = E->scratch.as<unsigned>();
+    CK(cudaMemsetAsync(g, 0, 8, E->st));
+    const bool cosine = E->distance == B200_DIST_COSINE;
+    if (cosine) E->obj_norms.ensure(sizeof(float) * std::max<int64_t>(n, 1));
+    if (n > 0)
+        row_stats_kernel<<<grid_for(n * 32, 256), 256, 0, E->st>>>(E->obj32_ptr, n, d, cosine ? 1 : 0,
+                                                                   cosine ? E->obj_norms.as<float>() : nullptr, g, g + 1);
+    CK(cudaGetLastError());
+    unsigned h[2];
+    CK(cudaMemcpyAsync(h, g, 8, cudaMemcpyDeviceToHost, E->st));
+    CK(cudaStreamSynchronize(E->st));
+    float absmax, maxnorm;
+    memcpy(&absmax, &h[0], 4);
+    memcpy(&maxnorm, &h[1], 4);
+    E->max_obj_norm = maxnorm;
+
+    if (tc_mode == B200_TC_OFF || E->cc_major != 10) {
+        E->tc_dtype = B200_TC_OFF;
+        return;
+    }
+    E->tc_dtype = (tc_mode == B200_TC_BF16) ? B200_TC_BF16 : B200_TC_FP16;
+    E->obj_exp = (E->tc_dtype == B200_TC_FP16) ? fp16_scale_exp(absmax) : 0;
+    E->n_obj_pad = round_up(std::max<int64_t>(n, 1), tc::TILE_N);
+    E->obj16.ensure((size_t)E->n_obj_pad * E->d_pad * 2);
+    const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
+    const int grid = grid_for(E->n_obj_pad * 32, 256);
+    if (E->tc_dtype == B200_TC_FP16)
+        convert_rows_kernel<__half, false><<<grid, 256, 0, E->st>>>(E->obj32_ptr, nullptr, n, E->n_obj_pad, d, E->d_pad, norms,
+                                                                    E->obj_exp, 1, E->obj16.as<__half>(), nullptr);
+    else
+        convert_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, E->st>>>(E->obj32_ptr, nullptr, n, E->n_obj_pad, d, E->d_pad,
+                                                                           norms, 0, 0, E->obj16.as<__nv_bfloat16>(), nullptr);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(E->st));
+    E->tm_obj_ok = make_tensor_map(&E->tm_obj_full, E->obj16.p, E->n_obj_pad, E->d_pad, E->tc_dtype == B200_TC_BF16);
+    if (!E->tm_obj_ok) E->tc_dtype = B200_TC_OFF;
+}
+
+struct TcPlan {
+    int s_sub, kblocks, n_stages, smem_bytes;
+    bool ok;
+};
+
+TcPlan plan_tc(int d_pad) {
+    TcPlan pl{};
+    pl.kblocks = d_pad / tc::KBLK;
+    for (int s = 2; s >= 1; --s) {
+        const int a = s * pl.kblocks * tc::BLK_BYTES;
+        const int lists = s * tc::TILE_M * 32 * 8;
+        const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
+        const int avail = tc::SMEM_LIMIT - fixed;
+        int stages = avail / tc::BLK_BYTES;
+        if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+        if (stages >= 3 || (s == 1 && stages >= 2)) {
+            pl.s_sub = s;
+            pl.n_stages = stages;
+            pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
+            pl.ok = true;
+            return pl;
+        }
+    }
+    pl.ok = false;
+    return pl;
+}
+
+uint32_t make_idesc(bool bf16) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // accumulator format: F32
+    d |= (bf16 ? 1u : 0u) << 7;         // A format
+    d |= (bf16 ? 1u : 0u) << 10;        // B format
+    // bits 13/14: no negate; bits 15/16: both operands K-major
+    d |= (uint32_t)(tc::TILE_N >> 3) << 17;
+    d |= (uint32_t)(tc::TILE_M >> 4) << 24;
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_rank_last_error(void) { return g_last_error.c_str(); }
+int b200_rank_abi_version(void) { return B200_RANK_ABI_VERSION; }
+
+int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_objects, int32_t d, int32_t distance,
+                     int32_t device, int32_t tc_mode, int32_t flags) {
+    if (!out) return fail(B200_E_INVALID, "b200_rank_create: out is NULL");
+    *out = nullptr;
+    if (n_objects < 0 || d <= 0 || (!objects && n_objects > 0))
+        return fail(B200_E_INVALID, "b200_rank_create: bad object matrix (n=%lld, d=%d)", (long long)n_objects, d);
+    if (n_objects >= (1ll << 31) - 1) return fail(B200_E_UNSUPPORTED, "b200_rank_create: more than 2^31-2 objects");
+    if (distance != B200_DIST_DOT && distance != B200_DIST_COSINE)
+        return fail(B200_E_INVALID, "b200_rank_create: distance must be B200_DIST_DOT or B200_DIST_COSINE");
+    if (tc_mode < B200_TC_AUTO || tc_mode > B200_TC_OFF) return fail(B200_E_INVALID, "b200_rank_create: bad tc_mode");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(B200_E_CUDA, "b200_rank_create: no CUDA device available (the engine has no CPU fallback)");
+    if (device < 0 || device >= n_dev) return fail(B200_E_INVALID, "b200_rank_create: device %d out of range", device);
+    b200_rank_engine* E = new (std::nothrow) b200_rank_engine();
+    if (!E) return fail(B200_E_NOMEM, "b200_rank_create: out of host memory");
+    try {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        E->device = device;
+        E->sm_count = prop.multiProcessorCount;
+        E->cc_major = prop.major;
+        E->cc_minor = prop.minor;
+        snprintf(E->dev_name, sizeof(E->dev_name), "%.127s", prop.name);
+        if (prop.major != 10) {
+            delete E;
+            return fail(B200_E_CUDA, "b200_rank_create: device %d is sm_%d%d; this library contains sm_100a code only",
+                        device, prop.major, prop.minor);
+        }
+        E->distance = distance;
+        E->n_obj = n_objects;
+        E->d = d;
+        E->d_pad = (int)round_up(d, tc::KBLK);
+        CK(cudaStreamCreateWithFlags(&E->st, cudaStreamNonBlocking));
+        for (auto& e : E->ev) CK(cudaEventCreate(&e));
+        CK(cudaMallocHost(&E->h_pinned, 64));
+        if (flags & B200_F_OBJECTS_ON_DEVICE) {
+            E->obj32_ptr = objects;
+            E->obj32_owned = false;
+        } else {
+            E->obj32.ensure(sizeof(float) * std::max<int64_t>(n_objects * d, 1));
+            if (n_objects > 0)
+                CK(cudaMemcpyAsync(E->obj32.p, objects, sizeof(float) * n_objects * d, cudaMemcpyHostToDevice, E->st));
+            E->obj32_ptr = E->obj32.as<float>();
+        }
+        if (tc_mode != B200_TC_OFF && E->d_pad > 1024) tc_mode = B200_TC_OFF;
+        prepare_objects(E, tc_mode);
+        if (E->tc_dtype != B200_TC_OFF) {
+            TcPlan pl = plan_tc(E->d_pad);
+            if (!pl.ok) {
+                E->tc_dtype = B200_TC_OFF;
+            } else {
+                CK(cudaFuncSetAttribute(tc::tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+            }
+        }
+        CK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    } catch (const CudaError& ce) {
+        int rc = fail(ce.e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "b200_rank_create: %s failed at line %d: %s",
+                      ce.what, ce.line, cudaGetErrorString(ce.e));
+        E->free_all();
+        delete E;
+        return rc;
+    }
+    *out = E;
+    return B200_OK;
+}
+
+int b200_rank_destroy(b200_rank_engine* E) {
+    if (!E) return B200_OK;
+    cudaSetDevice(E->device);
+    if (E->st) cudaStreamSynchronize(E->st);
+    E->free_all();
+    delete E;
+    return B200_OK;
+}
+
+int b200_rank_get_info(b200_rank_engine* E, b200_rank_info* info) {
+    if (!E || !info) return fail(B200_E_INVALID, "b200_rank_get_info: NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->abi_version = B200_RANK_ABI_VERSION;
+    info->device = E->device;
+    info->sm_count = E->sm_count;
+    info->cc_major = E->cc_major;
+    info->cc_minor = E->cc_minor;
+    info->tc_dtype = E->tc_dtype;
+    info->n_objects = E->n_obj;
+    info->d = E->d;
+    info->d_pad = E->d_pad;
+    info->hbm_bytes = (int64_t)E->hbm_bytes();
+    snprintf(info->device_name, sizeof(info->device_name), "%s", E->dev_name);
+    return B200_OK;
+}
+
+int b200_rank_set_subjects(b200_rank_engine* E, const float* subjects, int64_t n_subjects, int32_t on_device) {
+    if (!E) return fail(B200_E_INVALID, "b200_rank_set_subjects: engine is NULL");
+    if (n_subjects < 0 || (!subjects && n_subjects > 0)) return fail(B200_E_INVALID, "b200_rank_set_subjects: bad matrix");
+    std::lock_guard<std::mutex> lock(E->mu);
+    try {
+        CK(cudaSetDevice(E->device));
+        if (on_device) {
+            E->sub32_res_ptr = subjects;
+        } else {
+            E->sub32_res.ensure(sizeof(float) * std::max<int64_t>(n_subjects * E->d, 1));
+            if (n_subjects > 0)
+                CK(cudaMemcpyAsync(E->sub32_res.p, subjects, sizeof(float) * n_subjects * E->d, cudaMemcpyHostToDevice, E->st));
+            CK(cudaStreamSynchronize(E->st));
+            E->sub32_res_ptr = E->sub32_res.as<float>();
+        }
+        E->n_sub_res = n_subjects;
+    } catch (const CudaError& ce) {
+        return fail(ce.e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "b200_rank_set_subjects: %s failed: %s", ce.what,
+                    cudaGetErrorString(ce.e));
+    }
+    return B200_OK;
+}
+
+int b200_rank_set_id_offset(b200_rank_engine* E, int64_t offset) {
+    if (!E) return fail(B200_E_INVALID, "b200_rank_set_id_offset: engine is NULL");
+    if (offset < 0 || offset + E->n_obj >= (1ll << 31) - 1)
+        return fail(B200_E_INVALID, "b200_rank_set_id_offset: offset + n_objects must stay below 2^31-1");
+    std::lock_guard<std::mutex> lock(E->mu);
+    E->id_offset = offset;
+    return B200_OK;
+}
+
+int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stats* stats) {
+    if (!E || !q) return fail(B200_E_INVALID, "b200_rank_topk: NULL argument");
+    if (q->n_rows < 0) return fail(B200_E_INVALID, "b200_rank_topk: n_rows < 0");
+    if (q->k <= 0) return fail(B200_E_INVALID, "b200_rank_topk: k must be positive");
+    if (!q->subjects && !q->subject_ids) return fail(B200_E_INVALID, "b200_rank_topk: neither subjects nor subject_ids given");
+    if (!q->subjects && !E->sub32_res_ptr)
+        return fail(B200_E_INVALID, "b200_rank_topk: subject_ids given but b200_rank_set_subjects was never called");
+    if (q->subjects && q->subject_ids && q->n_subjects_total <= 0)
+        return fail(B200_E_INVALID, "b200_rank_topk: subjects + subject_ids need n_subjects_total");
+    if (q->whitelist && q->n_whitelist < 0) return fail(B200_E_INVALID, "b200_rank_topk: n_whitelist < 0");
+    if (q->n_rows > 0 && (!q->out_ids || !q->out_scores || !q->out_counts))
+        return fail(B200_E_INVALID, "b200_rank_topk: output pointers are NULL");
+    if (q->n_rows >= (1ll << 31) - 64) return fail(B200_E_UNSUPPORTED, "b200_rank_topk: more than 2^31 rows per call");
+    if ((q->flags & B200_Q_FORCE_EXACT) && (q->flags & B200_Q_FORCE_TC))
+        return fail(B200_E_INVALID, "b200_rank_topk: FORCE_EXACT and FORCE_TC are exclusive");
+
+    std::lock_guard<std::mutex> lock(E->mu);
+    b200_rank_stats S;
+    memset(&S, 0, sizeof(S));
+    const int64_t n_rows = q->n_rows;
+    const int64_t n_pos = q->whitelist ? q->n_whitelist : E->n_obj;
+    const int k_out = (int)std::min<int64_t>(q->k, n_pos);
+    S.k_out = k_out;
+    const bool in_dev = q->flags & B200_Q_INPUTS_ON_DEVICE;
+    const bool out_dev = q->flags & B200_Q_OUTPUTS_ON_DEVICE;
+    const int d = E->d;
+    if (n_rows == 0 || k_out <= 0) {
+        if (stats) *stats = S;
+        return B200_OK;
+    }
+    try {
+        CK(cudaSetDevice(E->device));
+        cudaStream_t st = E->st;
+        cudaStream_t user = reinterpret_cast<cudaStream_t>(q->stream);
+        if (user && (in_dev || out_dev)) {
+            CK(cudaEventRecord(E->ev[6], user));
+            CK(cudaStreamWaitEvent(st, E->ev[6], 0));
+        }
+        CK(cudaEventRecord(E->ev[0], st));
+
+        // ---------------- stage inputs
+        const float* sub32 = nullptr;
+        const int64_t* rowmap = nullptr;
+        auto stage = [&](DevBuf& buf, const void* src, size_t bytes) -> const void* {
+            if (in_dev) return src;
+            buf.ensure(std::max<size_t>(bytes, 16));
+            if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+            S.h2d_bytes += (int64_t)bytes;
+            return buf.p;
+        };
+        if (q->subjects) {
+            const int64_t rows_in = q->subject_ids ? q->n_subjects_total : n_rows;
+            sub32 = (const float*)stage(E->sub32, q->subjects, sizeof(float) * rows_in * d);
+        } else {
+            sub32 = E->sub32_res_ptr;
+        }
+        if (q->subject_ids) rowmap = (const int64_t*)stage(E->rowmap, q->subject_ids, sizeof(int64_t) * n_rows);
+        const int64_t* indptr = nullptr;
+        const int32_t* indices = nullptr;
+        if (q->csr_indptr) {
+            int64_t nnz = 0;
+            if (in_dev) {
+                CK(cudaMemcpyAsync(E->h_pinned, q->csr_indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                memcpy(&nnz, E->h_pinned, sizeof(int64_t));
+            } else {
+                nnz = q->csr_indptr[n_rows];
+            }
+            if (nnz < 0) return fail(B200_E_INVALID, "b200_rank_topk: csr_indptr[n_rows] < 0");
+            if (nnz > 0 && !q->csr_indices) return fail(B200_E_INVALID, "b200_rank_topk: csr_indices is NULL");
+            indptr = (const int64_t*)stage(E->indptr, q->csr_indptr, sizeof(int64_t) * (n_rows + 1));
+            indices = (const int32_t*)stage(E->indices, q->csr_indices, sizeof(int32_t) * nnz);
+            if (nnz == 0) indptr = nullptr;  // an all-empty filter is no filter (cf. rank_implicit.py:169-173)
+        }
+        const int32_t* wl = nullptr;
+        if (q->whitelist) wl = (const int32_t*)stage(E->wl, q->whitelist, sizeof(int32_t) * n_pos);
+        CK(cudaEventRecord(E->ev[1], st));
+
+        // ---------------- outputs
+        int32_t* o_ids;
+        float* o_scores;
+        int32_t* o_counts;
+        if (out_dev) {
+            o_ids = q->out_ids;
+            o_scores = q->out_scores;
+            o_counts = q->out_counts;
+        } else {
+            E->out_ids.ensure(sizeof(int32_t) * n_rows * k_out);
+            E->out_scores.ensure(sizeof(float) * n_rows * k_out);
+            E->out_counts.ensure(sizeof(int32_t) * n_rows);
+            o_ids = E->out_ids.as<int32_t>();
+            o_scores = E->out_scores.as<float>();
+            o_counts = E->out_counts.as<int32_t>();
+        }
+        init_outputs_kernel<<<grid_for(std::max<int64_t>(n_rows * k_out, n_rows), 256), 256, 0, st>>>(o_ids, o_scores, o_counts,
+                                                                                                   n_rows, k_out);
+        CK(cudaGetLastError());
+        S.n_launches++;
+
+        const bool cosine = E->distance == B200_DIST_COSINE;
+        const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
+
+        // exhaustive fp64 passes over `n_sel` rows (rows_dev == nullptr: all rows)
+        auto run_exact = [&](const int32_t* rows_dev, int64_t n_sel, bool timed) {
+            const int64_t tiles_total = (n_pos + 31) / 32;
+            const int blocks_x = grid_for(n_sel, EX_ROWS);
+            int n_splits = (2 * E->sm_count + blocks_x - 1) / blocks_x;
+            n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_splits, tiles_total / 64));
+            n_splits = std::min(n_splits, 1024);
+            E->part_scores.ensure(sizeof(float) * (size_t)n_splits * n_sel * LIST_LEN);
+            E->part_ids.ensure(sizeof(int32_t) * (size_t)n_splits * n_sel * LIST_LEN);
+            for (int k0 = 0; k0 < k_out; k0 += 32) {
+                const int kp = std::min(32, k_out - k0);
+                ExactParams p{};
+                p.subjects = sub32;
+                p.row_map = rowmap;
+                p.rows = rows_dev;
+                p.n_sel_dev = nullptr;
+                p.n_sel = n_sel;
+                p.objects = E->obj32_ptr;
+                p.pos2obj = wl;
+                p.n_pos = n_pos;
+                p.d = d;
+                p.obj_norms = norms;
+                p.indptr = indptr;
+                p.indices = indices;
+                p.id_off = (int32_t)E->id_offset;
+                p.k_out = k_out;
+                p.k0 = k0;
+                p.kp = kp;
+                p.out_ids = o_ids;
+                p.out_scores = o_scores;
+                p.out_counts = o_counts;
+                p.part_scores = E->part_scores.as<float>();
+                p.part_ids = E->part_ids.as<int32_t>();
+                p.part_stride_rows = n_sel;
+                if (timed && k0 == 0) CK(cudaEventRecord(E->ev[2], st));
+                exact_topk_kernel<<<dim3(blocks_x, n_splits), EX_THREADS, 0, st>>>(p);
+                CK(cudaGetLastError());
+                if (timed && k0 == 0) CK(cudaEventRecord(E->ev[3], st));
+                SelectParams sp{};
+                sp.in_scores = E->part_scores.as<float>();
+                sp.in_ids = E->part_ids.as<int32_t>();
+                sp.in_counts = nullptr;
+                sp.n_lists = n_splits;
+                sp.L = LIST_LEN;
+                sp.n_sel = n_sel;
+                sp.list_stride_rows = n_sel;
+                sp.rows = rows_dev;
+                sp.k_out = k_out;
+                sp.k0 = k0;
+                sp.kp = kp;
+                sp.out_ids = o_ids;
+                sp.out_scores = o_scores;
+                sp.out_counts = o_counts;
+                select_kernel<false><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
+                CK(cudaGetLastError());
+                S.n_launches += 2;
+            }
+            S.n_splits = n_splits;
+        };
+
+        // ---------------- path choice
+        TcPlan pl = plan_tc(E->d_pad);
+        int k_cand = 0;
+        if (k_out <= 10)
+            k_cand = 16;
+        else if (k_out <= 24)
+            k_cand = 32;
+        if (E->tc_dtype == B200_TC_BF16 && k_out <= 24) k_cand = 32;
+        bool use_tc = E->tc_dtype != B200_TC_OFF && pl.ok && k_cand > 0 && !(q->flags & B200_Q_FORCE_EXACT) &&
+                      n_pos >= (int64_t)k_cand * 4;
+        if (use_tc && !(q->flags & B200_Q_FORCE_TC)) {
+            // tiny problems are cheaper (and exercised) on the exhaustive kernel
+            if ((double)n_rows * (double)n_pos < 4.0e6) use_tc = false;
+        }
+        if ((q->flags & B200_Q_FORCE_TC) && !use_tc)
+            return fail(B200_E_UNSUPPORTED, "b200_rank_topk: tensor-core path unavailable (tc_dtype=%d, k=%d, d_pad=%d, n_pos=%lld)",
+                        E->tc_dtype, k_out, E->d_pad, (long long)n_pos);
+
+        if (!use_tc) {
+            S.path = 0;
+            run_exact(nullptr, n_rows, true);
+        } else {
+            S.path = 1;
+            S.tc_dtype = E->tc_dtype;
+            S.k_cand = k_cand;
+            const bool bf16 = E->tc_dtype == B200_TC_BF16;
+            const int rows_per_cta = pl.s_sub * tc::TILE_M;
+            const int64_t rows_pad = round_up(n_rows, rows_per_cta);
+            // subjects -> 16-bit, per-row power-of-two scale
+            E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
+            E->row_exp.ensure(sizeof(int32_t) * rows_pad);
+            {
+                const int grid = grid_for(rows_pad * 32, 256);
+                if (!bf16)
+                    convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(sub32, rowmap, n_rows, rows_pad, d, E->d_pad, nullptr, 0, 1,
+                                                                            E->sub16.as<__half>(), E->row_exp.as<int32_t>());
+                else
+                    convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(sub32, rowmap, n_rows, rows_pad, d, E->d_pad, nullptr,
+                                                                                   0, 0, E->sub16.as<__nv_bfloat16>(),
+                                                                                   E->row_exp.as<int32_t>());
+                CK(cudaGetLastError());
+                S.n_launches++;
+            }
+            // objects: resident 16-bit copy, or a whitelist gather of it
+            CUtensorMap tm_obj = E->tm_obj_full;
+            if (wl) {
+                const int64_t npad = round_up(n_pos, tc::TILE_N);
+                E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
+                const int chunks = E->d_pad * 2 / 16;
+                gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), wl, n_pos, npad, chunks,
+                                                                                 E->obj16_wl.as<uint4>());
+                CK(cudaGetLastError());
+                S.n_launches++;
+                if (!make_tensor_map(&tm_obj, E->obj16_wl.p, npad, E->d_pad, bf16))
+                    return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (whitelist objects)");
+            }
+            CUtensorMap tm_sub;
+            if (!make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
+                return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (subjects)");
+
+            tc::TcParams tp{};
+            tp.s_sub = pl.s_sub;
+            tp.kblocks = pl.kblocks;
+            tp.n_stages = pl.n_stages;
+            tp.k_cand = k_cand;
+            tp.n_rows = n_rows;
+            tp.n_pos = n_pos;
+            tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
+            tp.n_obj_tiles = (int)((n_pos + tc::TILE_N - 1) / tc::TILE_N);
+            // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
+            int best_splits = 1;
+            double best_eff = -1.0;
+            const int max_splits = std::max(1, std::min(16, tp.n_obj_tiles / 32));
+            for (int s = 1; s <= max_splits; ++s) {
+                const double work = (double)tp.n_row_tiles * s;
+                const double waves = std::ceil(work / E->sm_count);
+                const double eff = work / (waves * E->sm_count) - 0.004 * (s - 1);
+                if (eff > best_eff + 1e-9) {
+                    best_eff = eff;
+                    best_splits = s;
+                }
+            }
+            tp.n_splits = best_splits;
+            tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
+            tp.idesc = make_idesc(bf16);
+            tp.pos2obj = wl;
+            tp.indptr = indptr;
+            tp.indices = indices;
+            tp.id_off = (int32_t)E->id_offset;
+            E->cand_scores.ensure(sizeof(float) * (size_t)best_splits * rows_pad * 32);
+            E->cand_ids.ensure(sizeof(int32_t) * (size_t)best_splits * rows_pad * 32);
+            E->cand_counts.ensure(sizeof(int32_t) * (size_t)best_splits * rows_pad);
+            tp.cand_scores = E->cand_scores.as<float>();
+            tp.cand_ids = E->cand_ids.as<int32_t>();
+            tp.cand_counts = E->cand_counts.as<int32_t>();
+            tp.rows_pad = rows_pad;
+            S.n_splits = best_splits;
+            const int n_work = tp.n_row_tiles * tp.n_splits;
+            const int grid = std::min(n_work, E->sm_count);
+            CK(cudaEventRecord(E->ev[2], st));
+            tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(E->ev[3], st));
+            S.n_launches++;
+
+            // fp64 re-score of the candidates + certificate
+            E->fb_rows.ensure(sizeof(int32_t) * (n_rows + 1));
+            int32_t* fb_count = E->fb_rows.as<int32_t>() + n_rows;
+            CK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
+            SelectParams sp{};
+            sp.in_scores = tp.cand_scores;
+            sp.in_ids = tp.cand_ids;
+            sp.in_counts = tp.cand_counts;
+            sp.n_lists = best_splits;
+            sp.L = 32;
+            sp.n_sel = n_rows;
+            sp.list_stride_rows = rows_pad;
+            sp.k_out = k_out;
+            sp.k0 = 0;
+            sp.kp = k_out;
+            sp.out_ids = o_ids;
+            sp.out_scores = o_scores;
+            sp.out_counts = o_counts;
+            sp.subjects = sub32;
+            sp.row_map = rowmap;
+            sp.objects = E->obj32_ptr;
+            sp.obj_norms = norms;
+            sp.d = d;
+            sp.k_cand = k_cand;
+            sp.row_exp = E->row_exp.as<int32_t>();
+            sp.obj_exp = E->obj_exp;
+            const double rho = bf16 ? 0.001953125 /*2^-9*/ : 0.00048828125 /*2^-11*/;
+            sp.eps_rel = (float)(2.0 * rho + rho * rho + (double)E->d_pad * 4.76837158e-7 /*2^-21*/ +
+                                 std::sqrt((double)d) * 1.4551915e-11 /*2^-36*/);
+            sp.max_obj_norm = E->max_obj_norm;
+            sp.fb_count = fb_count;
+            sp.fb_rows = E->fb_rows.as<int32_t>();
+            const size_t sel_smem = (size_t)SEL_WARPS * d * sizeof(float);
+            if (sel_smem > 64 * 1024) return fail(B200_E_UNSUPPORTED, "b200_rank_topk: d too large for the re-score kernel");
+            select_kernel<true><<<grid_for(n_rows, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
+            CK(cudaGetLastError());
+            S.n_launches++;
+            CK(cudaMemcpyAsync(E->h_pinned, fb_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const int64_t n_fb = E->h_pinned[0];
+            S.n_fallback_rows = n_fb;
+            if (n_fb > 0) run_exact(E->fb_rows.as<int32_t>(), n_fb, false);
+        }
+
+        // ---------------- results back
+        if (E->id_offset != 0) {
+            add_offset_kernel<<<grid_for(n_rows * k_out, 256), 256, 0, st>>>(o_ids, n_rows * k_out, (int32_t)E->id_offset);
+            CK(cudaGetLastError());
+            S.n_launches++;
+        }
+        CK(cudaEventRecord(E->ev[4], st));
+        if (!out_dev) {
+            CK(cudaMemcpyAsync(q->out_ids, o_ids, sizeof(int32_t) * n_rows * k_out, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(q->out_scores, o_scores, sizeof(float) * n_rows * k_out, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(q->out_counts, o_counts, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, st));
+            S.d2h_bytes = (int64_t)(n_rows * k_out * 8 + n_rows * 4);
+        }
+        CK(cudaEventRecord(E->ev[5], st));
+        if (user && out_dev) {
+            CK(cudaEventRecord(E->ev[7], st));
+            CK(cudaStreamWaitEvent(user, E->ev[7], 0));
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&S.ms_total, E->ev[0], E->ev[5]));
+        CK(cudaEventElapsedTime(&S.ms_h2d, E->ev[0], E->ev[1]));
+        CK(cudaEventElapsedTime(&S.ms_main, E->ev[2], E->ev[3]));
+        CK(cudaEventElapsedTime(&S.ms_d2h, E->ev[4], E->ev[5]));
+    } catch (const CudaError& ce) {
+        return fail(ce.e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "b200_rank_topk: %s failed at line %d: %s", ce.what,
+                    ce.line, cudaGetErrorString(ce.e));
+    }
+    if (stats) *stats = S;
+    return B200_OK;
+}
+
+int b200_rank_merge(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids,
+                    const float* scores, const int32_t* counts, int32_t* out_ids, float* out_scores, int32_t* out_counts) {
+    if (n_lists <= 0 || n_rows < 0 || k <= 0 || !ids || !scores || !counts || !out_ids || !out_scores || !out_counts)
+        return fail(B200_E_INVALID, "b200_rank_merge: bad arguments");
+    if (n_rows == 0) return B200_OK;
+    try {
+        CK(cudaSetDevice(device));
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        init_outputs_kernel<<<grid_for(n_rows * k, 256), 256, 0, st>>>(out_ids, out_scores, out_counts, n_rows, k);
+        CK(cudaGetLastError());
+        for (int k0 = 0; k0 < k; k0 += 32) {
+            SelectParams sp{};
+            sp.in_scores = scores;
+            sp.in_ids = ids;
+            sp.in_counts = counts;
+            sp.n_lists = n_lists;
+            sp.L = k;
+            sp.n_sel = n_rows;
+            sp.list_stride_rows = n_rows;
+            sp.k_out = k;
+            sp.k0 = k0;
+            sp.kp = std::min(32, k - k0);
+            sp.out_ids = out_ids;
+            sp.out_scores = out_scores;
+            sp.out_counts = out_counts;
+            select_kernel<false><<<grid_for(n_rows, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
+            CK(cudaGetLastError());
+        }
+    } catch (const CudaError& ce) {
+        return fail(B200_E_CUDA, "b200_rank_merge: %s failed: %s", ce.what, cudaGetErrorString(ce.e));
+    }
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,385 @@
+// Fused tensor-core scoring + streaming top-K' candidate selection for sm_100a (tcgen05 / TMEM / TMA).
+//
+// One persistent CTA per SM.  A work item = (subject tile of S*128 rows, object split).  The subject tile stays
+// resident in shared memory; object tiles of 128 rows are streamed through a TMA -> mbarrier ring in 64-column
+// (128-byte, SWIZZLE_128B) blocks; `tcgen05.mma` (M=128, N=128, K=16, fp16/bf16 -> fp32) accumulates each
+// [128 x 128] score tile in TMEM (2 buffers x S sub-tiles x 128 columns = up to all 512 columns); the epilogue
+// warps read the accumulators back with `tcgen05.ld` (thread = subject row, 32 consecutive objects per load),
+// compare against the row's running K'-th best score and only on a hit (rare after warm-up) look the object up in
+// the row's `filter_pairs_csr` slice and insert it into the row's sorted candidate list (shared memory, one
+// list entry per lane).  Score rows never reach HBM: only K' (score, id) pairs per row and split are written.
+//
+// This replaces `scores = query @ items.T` + mask + select of implicit's top-k (call site
+// rectools/models/rank/rank_implicit.py:264-272, :175-182) and `TorchRanker.rank`'s batched matmul / masked_fill /
+// torch.topk (rectools/models/rank/rank_torch.py:133-152) as a CANDIDATE generator; exact scores and the final
+// order come from select_kernel<true> (select.cuh).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace tc {
+
+constexpr int TILE_M = 128;              // subject rows per sub-tile = TMEM lanes
+constexpr int TILE_N = 128;              // objects per tile = TMEM columns per accumulator
+constexpr int KBLK = 64;                 // 16-bit elements per shared-memory block row (128 B, one swizzle atom)
+constexpr int BLK_BYTES = 128 * KBLK * 2;  // 16 KiB: [128 rows][128 B]
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 384;         // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4-11: epilogue
+constexpr int EPI_WARP0 = 4;
+constexpr int MAX_STAGES = 12;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 232448;       // 227 KiB
+
+struct TcParams {
+    int32_t s_sub;            // sub-tiles per CTA (1 or 2)
+    int32_t kblocks;          // d_pad / 64
+    int32_t n_stages;         // object ring depth (blocks of 16 KiB)
+    int32_t k_cand;           // K' <= 32
+    int64_t n_rows;           // valid subject rows
+    int64_t n_pos;            // valid object positions
+    int32_t n_row_tiles;
+    int32_t n_splits;
+    int32_t n_obj_tiles;
+    int32_t tiles_per_split;
+    uint32_t idesc;           // UMMA instruction descriptor
+    const int32_t* pos2obj;   // nullable whitelist map
+    const int64_t* indptr;    // nullable CSR filter by subject row
+    const int32_t* indices;
+    int32_t id_off;           // global id = local object id + id_off (CSR column ids are global)
+    float* cand_scores;       // [n_splits][rows_pad][32]
+    int32_t* cand_ids;
+    int32_t* cand_counts;     // [n_splits][rows_pad]
+    int64_t rows_pad;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Wait for the phase with the given parity to complete.  A watchdog turns a protocol bug into a trap, not a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > (1ll << 33)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tiled TMA load global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x N x 16, issued by one thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (base_lane + i), columns [c, c+32).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address  [0,14)
+    d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant__ CUtensorMap tm_obj, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int S = p.s_sub, KB = p.kblocks, NS = p.n_stages;
+    uint8_t* sA = smem;                                      // [S][KB] blocks
+    uint8_t* sB = sA + (size_t)S * KB * BLK_BYTES;           // [NS] blocks
+    float* sLs = reinterpret_cast<float*>(sB + (size_t)NS * BLK_BYTES);  // [S*128][32] candidate scores
+    int* sLi = reinterpret_cast<int*>(sLs + S * TILE_M * 32);            // [S*128][32] candidate ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sLi + S * TILE_M * 32);
+    // barrier map: full[0..MAX), empty[MAX..2MAX), a_full, a_empty, t_full[2], t_empty[2]
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = smem_u32(bars + MAX_STAGES);
+    const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES);
+    const uint32_t bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 1);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES + 2);
+    const uint32_t bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        mbar_init(bar_afull, 1);
+        mbar_init(bar_aempty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4 * S);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tm_sub);
+        tma_prefetch_desc(&tm_obj);
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_work = p.n_row_tiles * p.n_splits;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer (one lane)
+        if (lane == 0) {
+            uint32_t it = 0, work_it = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
+                const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
+                if (work_it > 0) mbar_wait(bar_aempty, (work_it - 1) & 1);  // previous tile's MMAs are done with sA
+                mbar_arrive_expect_tx(bar_afull, (uint32_t)(S * KB * BLK_BYTES));
+                for (int s = 0; s < S; ++s)
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_2d(smem_u32(sA + (size_t)(s * KB + kb) * BLK_BYTES), &tm_sub, bar_afull, kb * KBLK,
+                                    (rt * S + s) * TILE_M);
+                for (int t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const uint32_t stage = it % NS, ph = (it / NS) & 1;
+                        mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, BLK_BYTES);
+                        tma_load_2d(smem_u32(sB + (size_t)stage * BLK_BYTES), &tm_obj, bar_full + 8 * stage, kb * KBLK,
+                                    t * TILE_N);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (one lane)
+        if (lane == 0) {
+            uint32_t it = 0, tile_it = 0, work_it = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
+                const int split = w / p.n_row_tiles;
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
+                mbar_wait(bar_afull, work_it & 1);
+                tc_fence_after();
+                for (int t = t0; t < t1; ++t, ++tile_it) {
+                    const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * buf, tph ^ 1);  // epilogue has drained this accumulator pair
+                    tc_fence_after();
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const uint32_t stage = it % NS, ph = (it / NS) & 1;
+                        mbar_wait(bar_full + 8 * stage, ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * BLK_BYTES));
+                        for (int s = 0; s < S; ++s) {
+                            const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)(s * KB + kb) * BLK_BYTES));
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * S + s) * TILE_N);
+#pragma unroll
+                            for (int k4 = 0; k4 < KBLK / UMMA_K; ++k4) {
+                                // +32 B per K step inside the 128 B swizzle atom = +2 in the (addr >> 4) field
+                                umma_f16(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
+                                         (uint32_t)((kb | k4) != 0));
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * stage);  // ring slot is free once these MMAs retire
+                    }
+                    umma_commit(bar_tfull + 8 * buf);  // accumulators of this tile are complete
+                }
+                umma_commit(bar_aempty);
+            }
+        }
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * S) {
+        // ===================================================================== epilogue: select candidates
+        const int ew = warp - EPI_WARP0;
+        const int s = ew >> 2, quarter = ew & 3;  // quarter == warp % 4: the TMEM lanes this warp may read
+        const int wrow0 = s * TILE_M + quarter * 32;  // first CTA-local row of this warp
+        float* myLs = sLs + (size_t)wrow0 * 32;
+        int* myLi = sLi + (size_t)wrow0 * 32;
+        const int kc = p.k_cand;
+        uint32_t tile_it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
+            const int64_t grow0 = (int64_t)rt * S * TILE_M + wrow0;  // global row of lane 0
+            const int64_t grow = grow0 + lane;
+            const bool row_ok = grow < p.n_rows;
+            for (int r = 0; r < 32; ++r) {
+                myLs[r * 32 + lane] = -INFINITY;
+                myLi[r * 32 + lane] = B200_PAD_ID;
+            }
+            __syncwarp();
+            float thr = row_ok ? -INFINITY : INFINITY;  // padded rows never produce candidates
+            int64_t flo = 0, fhi = 0;
+            if (row_ok && p.indptr) {
+                flo = p.indptr[grow];
+                fhi = p.indptr[grow + 1];
+            }
+            for (int t = t0; t < t1; ++t, ++tile_it) {
+                const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
+                mbar_wait(bar_tfull + 8 * buf, tph);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * S + s) * TILE_N);
+#pragma unroll 1
+                for (int cc = 0; cc < TILE_N / 32; ++cc) {
+                    float v[32];
+                    tmem_ld32(tbase + cc * 32, v);
+                    float m0 = max3(v[0], v[1], v[2]), m1 = max3(v[3], v[4], v[5]);
+                    float m2 = max3(v[6], v[7], v[8]), m3 = max3(v[9], v[10], v[11]);
+                    float m4 = max3(v[12], v[13], v[14]), m5 = max3(v[15], v[16], v[17]);
+                    float m6 = max3(v[18], v[19], v[20]), m7 = max3(v[21], v[22], v[23]);
+                    float m8 = max3(v[24], v[25], v[26]), m9 = max3(v[27], v[28], v[29]);
+                    m0 = max3(m0, m1, m2);
+                    m3 = max3(m3, m4, m5);
+                    m6 = max3(m6, m7, m8);
+                    m9 = max3(m9, v[30], v[31]);
+                    const float mx = fmaxf(max3(m0, m3, m6), m9);
+                    if (__any_sync(B200_FULL_MASK, mx > thr)) {
+                        // ---- slow path: some row of this warp has a score above its running threshold
+                        const int64_t pos0 = (int64_t)t * TILE_N + cc * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            bool c = v[j] > thr;
+                            int obj = 0;
+                            if (c) {
+                                const int64_t pos = pos0 + j;
+                                c = pos < p.n_pos;
+                                if (c) {
+                                    obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
+                                    if (p.indptr) c = !csr_contains(p.indices, flo, fhi, obj + p.id_off);
+                                }
+                            }
+                            unsigned m = __ballot_sync(B200_FULL_MASK, c);
+                            while (m) {
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float cs = __shfl_sync(B200_FULL_MASK, v[j], src);
+                                const int ci = __shfl_sync(B200_FULL_MASK, obj, src);
+                                float es = myLs[src * 32 + lane];
+                                int ei = myLi[src * 32 + lane];
+                                const int ins = __popc(__ballot_sync(B200_FULL_MASK, es >= cs));
+                                const float us = __shfl_up_sync(B200_FULL_MASK, es, 1);
+                                const int ui = __shfl_up_sync(B200_FULL_MASK, ei, 1);
+                                if (lane == ins) {
+                                    es = cs;
+                                    ei = ci;
+                                } else if (lane > ins) {
+                                    es = us;
+                                    ei = ui;
+                                }
+                                myLs[src * 32 + lane] = es;
+                                myLi[src * 32 + lane] = ei;
+                                const float nthr = __shfl_sync(B200_FULL_MASK, es, kc - 1);
+                                if (lane == src) thr = nthr;
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            }
+            // ---- write this warp's 32 candidate lists (coalesced 128 B rows)
+            for (int r = 0; r < 32; ++r) {
+                const int64_t gr = grow0 + r;
+                if (gr >= p.n_rows) break;
+                const float es = myLs[r * 32 + lane];
+                const int ei = myLi[r * 32 + lane];
+                const int64_t o = ((int64_t)split * p.rows_pad + gr) * 32 + lane;
+                const bool keep = lane < kc;
+                p.cand_scores[o] = keep ? es : -INFINITY;
+                p.cand_ids[o] = keep ? ei : B200_PAD_ID;
+                const int cnt = __popc(__ballot_sync(B200_FULL_MASK, keep && ei != B200_PAD_ID));
+                if (lane == 0) p.cand_counts[(int64_t)split * p.rows_pad + gr] = cnt;
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+}  // namespace b200

@@ -35,22 +35,13 @@ def synth_factors(n_users, n_items, d, seed=0):
 
 
 def synth_viewed_csr(n_users, n_items, per_user, seed=2):
-    """`per_user` distinct viewed items per user, sorted indices, int32 indices / int64 indptr, data = ones."""
+    """~`per_user` viewed items per user (uniform draws, sorted within a row; rare duplicates are kept -- the filter
+    is a set-membership test so they are harmless), int32 indices / int64 indptr, data = ones."""
     rng = np.random.default_rng(seed)
-    per_user = min(per_user, n_items)
-    # sample without replacement per row via random keys on a candidate superset (fast, vectorised)
-    cand = rng.integers(0, n_items, size=(n_users, per_user * 2 + 8), dtype=np.int64)
-    cand.sort(axis=1)
-    rows = []
-    indptr = np.zeros(n_users + 1, dtype=np.int64)
-    for r in range(n_users):
-        u = np.unique(cand[r])
-        if len(u) > per_user:
-            u = np.sort(rng.choice(u, size=per_user, replace=False))
-        rows.append(u.astype(np.int32))
-        indptr[r + 1] = indptr[r] + len(u)
-    indices = np.concatenate(rows) if rows else np.empty(0, np.int32)
-    return sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(n_users, n_items))
+    cols = rng.integers(0, n_items, size=(n_users, per_user), dtype=np.int32)
+    cols.sort(axis=1)
+    indptr = np.arange(n_users + 1, dtype=np.int64) * per_user
+    return sparse.csr_matrix((np.ones(cols.size, np.float32), cols.reshape(-1), indptr), shape=(n_users, n_items))
 
 
 def ragged_to_padded(subjects, ids, scores, subject_ids, k):

@@ -1,0 +1,274 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via B200Ranker / Engine) against the oracle and the golden
+fixtures generated from the unmodified reference.  Bar: object ids bit-exact; scores to fp32 rounding (the engine
+defines scores as the fp64-accumulated dot rounded once to fp32, the oracle's accum="f64" mode)."""
+import os
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle.topk_oracle import rank_oracle
+from tests.helpers import (
+    assert_same_ranking,
+    golden_keys,
+    load_rank_case,
+    parse_key,
+    ragged_to_padded,
+    synth_factors,
+    synth_viewed_csr,
+)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rectools_b200
+
+    return rectools_b200
+
+
+# ------------------------------------------------------------------ reference known-answer vectors (test_rank.py:52-233)
+SUBJECTS = np.array([[-4, 0, 3], [0, 1, 2]])
+OBJECTS = np.array([[-4, 0, 3], [0, 2, 4], [1, 10, 100]])
+
+
+@pytest.mark.parametrize(
+    "distance, expected_recs, expected_scores",
+    (
+        ("dot", [2, 0, 1, 2, 1, 0], [296, 25, 12, 210, 10, 6]),
+        ("cosine", [0, 2, 1, 1, 2, 0], [1, 0.5890328, 0.5366563, 1, 0.9344414, 0.5366563]),
+        ("euclidean", [0, 1, 2, 1, 0, 2], [0, 4.58257569, 97.64220399, 2.23606798, 4.24264069, 98.41747812]),
+    ),
+)
+@pytest.mark.parametrize("dense", [True, False])
+def test_rank_known_answers(rb, distance, expected_recs, expected_scores, dense):
+    subj = SUBJECTS if dense else sparse.csr_matrix(SUBJECTS)
+    if not dense and distance != "dot":
+        with pytest.raises(ValueError):
+            rb.B200Ranker(distance, subj, OBJECTS)
+        return
+    ranker = rb.B200Ranker(distance, subj, OBJECTS)
+    users, recs, scores = ranker.rank(subject_ids=[0, 1], k=3)
+    np.testing.assert_equal(users, [0, 0, 0, 1, 1, 1])
+    np.testing.assert_equal(recs, expected_recs)
+    np.testing.assert_almost_equal(scores, expected_scores, decimal=5)
+
+
+@pytest.mark.parametrize(
+    "distance, expected_recs, expected_scores",
+    (
+        ("dot", [2, 1, 2, 0], [296, 12, 210, 6]),
+        ("cosine", [2, 1, 2, 0], [0.5890328, 0.5366563, 0.9344414, 0.5366563]),
+        ("euclidean", [1, 2, 0, 2], [4.58257569, 97.64220399, 4.24264069, 98.41747812]),
+    ),
+)
+def test_rank_with_filter_known_answers(rb, distance, expected_recs, expected_scores):
+    ui_csr = sparse.csr_matrix([[1, 0, 0], [0, 1, 0]])
+    _, recs, scores = rb.B200Ranker(distance, SUBJECTS, OBJECTS).rank([0, 1], k=3, filter_pairs_csr=ui_csr)
+    np.testing.assert_equal(recs, expected_recs)
+    np.testing.assert_almost_equal(scores, expected_scores, decimal=5)
+
+
+@pytest.mark.parametrize(
+    "distance, expected_recs, expected_scores",
+    (
+        ("dot", [2, 0, 2, 0], [296, 25, 210, 6]),
+        ("cosine", [0, 2, 2, 0], [1, 0.5890328, 0.9344414, 0.5366563]),
+        ("euclidean", [0, 2, 0, 2], [0, 97.64220399, 4.24264069, 98.41747812]),
+    ),
+)
+def test_rank_with_whitelist_known_answers(rb, distance, expected_recs, expected_scores):
+    _, recs, scores = rb.B200Ranker(distance, SUBJECTS, OBJECTS).rank([0, 1], k=3, sorted_object_whitelist=np.array([0, 2]))
+    np.testing.assert_equal(recs, expected_recs)
+    np.testing.assert_almost_equal(scores, expected_scores, decimal=5)
+
+
+def test_shape_mismatch_raises(rb):
+    ranker = rb.B200Ranker("dot", SUBJECTS, OBJECTS)
+    with pytest.raises(ValueError):
+        ranker.rank([0, 1], k=3, filter_pairs_csr=sparse.csr_matrix([[1, 0, 0]]))
+
+
+# ------------------------------------------------------------------ golden fixtures from the unmodified reference
+@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("force", ["default", "tc", "exact"])
+def test_golden_rankers(rb, case, force):
+    from rectools_b200 import _lib
+
+    inp, out, csr = load_rank_case(case)
+    rankers = {}
+    n_checked = 0
+    for key in golden_keys(out):
+        impl, dist, k, use_filter, use_wl = parse_key(key)
+        if impl == "torch" and dist == "euclidean":
+            continue  # cdist-based scores / -inf masking differ from the implicit contract (see test_oracle_golden.py)
+        if dist not in rankers:
+            rankers[dist] = rb.B200Ranker(dist, inp["subjects"], inp["objects"])
+        ranker = rankers[dist]
+        n_pos = len(inp["whitelist"]) if use_wl else inp["objects"].shape[0]
+        k_eff = n_pos if k is None else min(k, n_pos)
+        flags = 0
+        if force == "tc":
+            if k_eff > 24 or n_pos < 128:
+                continue
+            flags = _lib.Q_FORCE_TC
+        elif force == "exact":
+            flags = _lib.Q_FORCE_EXACT
+        sids, ids, scores, counts = ranker.rank_padded(
+            inp["subject_ids"], k, csr if use_filter else None, inp["whitelist"] if use_wl else None, flags=flags
+        )
+        if force == "tc":
+            assert ranker.last_stats["path"] == 1
+        subj, fids, fscores = rb.flatten_padded(sids, ids, scores, counts)
+        if dist == "cosine":
+            fscores = fscores / ranker.subjects_norms[subj]
+        elif dist == "euclidean":
+            fscores = np.sqrt(np.maximum(ranker.subjects_dots[subj] - fscores, 0)).astype(np.float32)
+        np.testing.assert_array_equal(subj, out[key + "|subjects"], err_msg=key)
+        atol = 2e-4 if dist == "euclidean" else 2e-6
+        assert_same_ranking(fids, fscores, out[key + "|ids"], out[key + "|scores"], tie_tol=2e-6, atol=atol, msg=key)
+        n_checked += 1
+    assert n_checked > 10
+
+
+def test_golden_puresvd_c1(rb, golden_dir):
+    """BASELINE config 1: factors of the reference's PureSVDModel(factors=32) on 6040x3706, K=10, filter_viewed."""
+    g = np.load(os.path.join(golden_dir, "puresvd_c1.npz"))
+    csr = sparse.csr_matrix(
+        (np.ones(len(g["csr_indices"]), np.float32), g["csr_indices"], g["csr_indptr"]), shape=tuple(g["csr_shape"])
+    )
+    ranker = rb.B200Ranker("dot", g["user_factors"], g["item_factors"])
+    for filt, pre in ((csr, "out_"), (None, "out_nf_")):
+        subj, ids, scores = ranker.rank(g["subject_ids"], 10, filt)
+        np.testing.assert_array_equal(subj, g[pre + "subjects"])
+        assert_same_ranking(ids, scores, g[pre + "ids"], g[pre + "scores"], tie_tol=2e-6, msg=pre)
+
+
+# ------------------------------------------------------------------ seeded random inputs vs the fp64 oracle
+@pytest.mark.parametrize(
+    "n_users, n_items, d, k, per_user, distance, tc_mode",
+    [
+        (2048, 50_000, 128, 10, 100, "dot", "auto"),
+        (2048, 50_000, 128, 10, 100, "cosine", "auto"),
+        (1024, 30_000, 128, 10, 50, "dot", "bf16"),
+        (777, 20_011, 64, 20, 30, "dot", "auto"),
+        (300, 9_001, 200, 5, 10, "cosine", "auto"),
+        (513, 12_345, 256, 20, 0, "dot", "auto"),
+        (64, 5_000, 32, 100, 40, "dot", "auto"),  # K > 32: multi-pass exhaustive kernel
+    ],
+)
+def test_random_vs_oracle(rb, n_users, n_items, d, k, per_user, distance, tc_mode):
+    from rectools_b200 import _lib
+
+    u, i = synth_factors(n_users, n_items, d, seed=n_users)
+    csr = synth_viewed_csr(n_users, n_items, per_user) if per_user else None
+    ranker = rb.B200Ranker(distance, u, i, tc_mode=tc_mode)
+    sids = np.arange(n_users)
+    for flags in ((_lib.Q_FORCE_TC if k <= 24 else 0), _lib.Q_FORCE_EXACT):
+        if flags == _lib.Q_FORCE_EXACT and n_users * n_items > 3e7:
+            sel = sids[:: max(1, n_users // 128)]
+        else:
+            sel = sids
+        sub_csr = csr[sel] if csr is not None else None
+        _, ids, scores, counts = ranker.rank_padded(sel, k, sub_csr, flags=flags)
+        assert (counts == k).all()
+        _, oid, osc = rank_oracle(distance, u, i, sel, k, sub_csr, accum="f64")
+        if distance == "cosine":
+            osc = osc * ranker.subjects_norms[np.repeat(sel, k)]  # engine scores are before the subject-norm division
+        np.testing.assert_array_equal(ids.reshape(-1), oid, err_msg=f"flags={flags} stats={ranker.last_stats}")
+        np.testing.assert_allclose(scores.reshape(-1), osc, rtol=3e-7, atol=1e-9)
+        if flags == _lib.Q_FORCE_TC:
+            assert ranker.last_stats["path"] == 1
+            assert ranker.last_stats["n_fallback_rows"] <= max(4, n_users // 50), ranker.last_stats
+
+
+def test_edge_cases(rb):
+    from rectools_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    n_users, n_items, d = 40, 700, 24
+    u = rng.standard_normal((n_users, d)).astype(np.float32)
+    i = rng.standard_normal((n_items, d)).astype(np.float32)
+    i[100:140] = i[100]  # 40 identical objects: ties must come out in ascending id order
+    i[300:320] = 0.0  # zero vectors (score exactly 0, COSINE norm guard)
+    u[7] = 0.0  # zero subject: every score ties at 0
+    dense = np.zeros((n_users, n_items), dtype=np.float32)
+    dense[3, :] = 1  # everything viewed -> no recommendations
+    dense[4, : n_items - 3] = 1  # only 3 candidates left -> fewer than k rows
+    dense[5, ::2] = 1
+    csr = sparse.csr_matrix(dense)
+    whitelist = np.sort(rng.choice(n_items, 333, replace=False))
+    for distance in ("dot", "cosine"):
+        ranker = rb.B200Ranker(distance, u, i)
+        for wl in (None, whitelist):
+            for k in (1, 10, 24, 33, None):
+                for flags in (0, _lib.Q_FORCE_TC, _lib.Q_FORCE_EXACT):
+                    n_pos = n_items if wl is None else len(wl)
+                    k_eff = n_pos if k is None else min(k, n_pos)
+                    if flags == _lib.Q_FORCE_TC and k_eff > 24:
+                        continue
+                    sids = np.arange(n_users)[::-1].copy()
+                    s1, r1, c1 = ranker.rank(sids, k, csr[sids], wl) if flags == 0 else (None, None, None)
+                    _, ids, scores, counts = ranker.rank_padded(sids, k, csr[sids], wl, flags=flags)
+                    subj, fids, fsc = rb.flatten_padded(sids, ids, scores, counts)
+                    if distance == "cosine":
+                        fsc = fsc / ranker.subjects_norms[subj]
+                    osubj, oid, osc = rank_oracle(distance, u, i, sids, k, csr[sids], wl, accum="f64")
+                    msg = f"{distance} wl={wl is not None} k={k} flags={flags}"
+                    np.testing.assert_array_equal(subj, osubj, err_msg=msg)
+                    np.testing.assert_array_equal(fids, oid, err_msg=msg)
+                    np.testing.assert_allclose(fsc, osc, rtol=1e-6, atol=1e-7, err_msg=msg)
+                    if s1 is not None:
+                        np.testing.assert_array_equal(r1, oid)
+    # empty subject list / k larger than the catalogue
+    ranker = rb.B200Ranker("dot", u, i[:5])
+    s, r, c = ranker.rank([], k=3)
+    assert len(s) == len(r) == len(c) == 0
+    s, r, c = ranker.rank([0, 1], k=50)
+    assert len(r) == 10
+    with pytest.raises(ValueError):
+        ranker.rank([0], k=0)
+
+
+def test_merge_matches_unsharded(rb):
+    """Item-sharded ranking: per-shard top-k with global ids + b200_rank_merge == ranking the whole catalogue."""
+    import torch
+
+    from rectools_b200 import _lib
+
+    n_users, n_items, d, k = 1000, 40_000, 64, 10
+    u, i = synth_factors(n_users, n_items, d, seed=11)
+    csr = synth_viewed_csr(n_users, n_items, 20)
+    full = rb.B200Ranker("dot", u, i)
+    _, ids_full, sc_full, cnt_full = full.rank_padded(np.arange(n_users), k, csr)
+    shards = 3
+    bounds = np.linspace(0, n_items, shards + 1).astype(int)
+    all_ids, all_sc, all_cnt = [], [], []
+    for s in range(shards):
+        lo, hi = bounds[s], bounds[s + 1]
+        eng = rb.Engine(i[lo:hi], cosine=False, id_offset=int(lo))
+        ids, sc, cnt = eng.topk(k, subjects=u, indptr=csr.indptr, indices=csr.indices)
+        assert ids[cnt > 0].min() >= lo and ids.max() < hi
+        all_ids.append(ids)
+        all_sc.append(sc)
+        all_cnt.append(cnt)
+        eng.close()
+    dev = torch.device("cuda:0")
+    t_ids = torch.from_numpy(np.stack(all_ids)).to(dev)
+    t_sc = torch.from_numpy(np.stack(all_sc)).to(dev)
+    t_cnt = torch.from_numpy(np.stack(all_cnt)).to(dev)
+    o_ids = torch.empty((n_users, k), dtype=torch.int32, device=dev)
+    o_sc = torch.empty((n_users, k), dtype=torch.float32, device=dev)
+    o_cnt = torch.empty((n_users,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    _lib.check(
+        _lib.load().b200_rank_merge(
+            0, torch.cuda.current_stream().cuda_stream, shards, n_users, k, t_ids.data_ptr(), t_sc.data_ptr(),
+            t_cnt.data_ptr(), o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(),
+        )
+    )
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o_ids.cpu().numpy(), ids_full)
+    np.testing.assert_array_equal(o_sc.cpu().numpy(), sc_full)
+    np.testing.assert_array_equal(o_cnt.cpu().numpy(), cnt_full)
