@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -623,11 +624,15 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             for (int s = 1; s <= max_splits; ++s) {
                 const double work = (double)tp.n_row_tiles * s;
                 const double waves = std::ceil(work / E->sm_count);
-                const double eff = work / (waves * E->sm_count) - 0.004 * (s - 1);
+                const double eff = work / (waves * E->sm_count) - 0.01 * (s - 1);
                 if (eff > best_eff + 1e-9) {
                     best_eff = eff;
                     best_splits = s;
                 }
+            }
+            if (const char* env = getenv("B200_TC_SPLITS")) {  // tuning / test hook
+                const int forced = atoi(env);
+                if (forced >= 1 && forced <= max_splits) best_splits = forced;
             }
             tp.n_splits = best_splits;
             tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;

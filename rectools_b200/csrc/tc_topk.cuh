@@ -79,8 +79,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (spin == 64) t0 = clock64();
-        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > (1ll << 33)) __trap();
+        if ((spin & 4095) == 4095) {
+            const long long now = clock64();
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > (1ll << 33))
+                __trap();
+        }
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -106,6 +111,16 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// One lane of the (converged) warp; the same lane every time, so tcgen05.commit tracks the MMAs it issued.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -124,8 +139,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (base_lane + i), columns [c, c+32).
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// The load is asynchronous: the registers are valid only after tmem_ld_wait() on the same array.
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -136,9 +151,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// Wait for every outstanding tcgen05.ld of this thread.  The registers are threaded through the asm as in/out
+// operands so that the compiler cannot schedule their first use above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // Shared-memory matrix descriptor: K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart.
@@ -153,6 +176,125 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// ------------------------------------------------------------------------------------------------ epilogue helpers
+// Per-row state of the streaming selection (registers of the thread that owns the row).
+struct RowState {
+    float thr;    // K'-th best approximate score so far (-inf until the list is full, +inf for padded rows)
+    int nv;       // next viewed global object id >= the stream position (B200_PAD_ID when the CSR row is exhausted)
+    int64_t cur;  // index of `nv` in csr indices
+    int64_t fhi;  // end of the row's CSR slice
+};
+
+// Objects are visited in ascending id order, so the filter_pairs_csr lookup is a merge, not a search: `nv` trails
+// the stream and is advanced only when a candidate reaches it (two linear steps, then lower_bound on the rest).
+__device__ __forceinline__ bool csr_is_viewed(const int32_t* __restrict__ indices, RowState& rs, int g) {
+    if (rs.nv < g) {
+#pragma unroll 1
+        for (int step = 0; step < 2 && rs.nv < g; ++step) {
+            ++rs.cur;
+            rs.nv = rs.cur < rs.fhi ? __ldg(indices + rs.cur) : B200_PAD_ID;
+        }
+        if (rs.nv < g) {
+            int64_t lo = rs.cur + 1, hi = rs.fhi;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(indices + mid) < g)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            rs.cur = lo;
+            rs.nv = lo < rs.fhi ? __ldg(indices + lo) : B200_PAD_ID;
+        }
+    }
+    return rs.nv == g;
+}
+
+// v[j] for a run-time j without local memory: 5-level select tree (31 SEL), cheaper than spilling the chunk.
+__device__ __forceinline__ float select32(const float (&v)[32], int j) {
+    float a[16], b[8], c[4], d[2];
+    const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = b3 ? c[2 * i + 1] : c[2 * i];
+    return b4 ? d[1] : d[0];
+}
+
+// Slow path of one chunk (compact on purpose: the unrolled per-column version thrashed the instruction cache).
+// Every lane builds the bit mask of its columns above the row threshold, then the warp drains the masks: each lane
+// takes its lowest pending column (ascending object order per row, as the CSR cursor needs), re-checks it against
+// the possibly raised threshold, drops padded / viewed objects, and the survivors are inserted one by one into
+// their row's sorted candidate list (warp-cooperative: one list entry per lane).
+__device__ __forceinline__ void scan_chunk(const float (&v)[32], int64_t pos0, const TcParams& p, float* myLs, int* myLi,
+                                        int lane, int kc, RowState& rs) {
+    unsigned hits = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) hits |= (v[j] > rs.thr) ? (1u << j) : 0u;
+    while (__any_sync(B200_FULL_MASK, hits != 0)) {
+        bool c = false;
+        float val = 0.f;
+        int obj = 0;
+        if (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            val = select32(v, j);
+            c = val > rs.thr;
+            if (c) {
+                const int64_t pos = pos0 + j;
+                c = pos < p.n_pos;
+                if (c) {
+                    obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
+                    c = !csr_is_viewed(p.indices, rs, obj + p.id_off);
+                }
+            }
+        }
+        unsigned m = __ballot_sync(B200_FULL_MASK, c);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cs = __shfl_sync(B200_FULL_MASK, val, src);
+            const int ci = __shfl_sync(B200_FULL_MASK, obj, src);
+            float es = myLs[src * 32 + lane];
+            int ei = myLi[src * 32 + lane];
+            const int ins = __popc(__ballot_sync(B200_FULL_MASK, es >= cs));
+            const float us = __shfl_up_sync(B200_FULL_MASK, es, 1);
+            const int ui = __shfl_up_sync(B200_FULL_MASK, ei, 1);
+            if (lane == ins) {
+                es = cs;
+                ei = ci;
+            } else if (lane > ins) {
+                es = us;
+                ei = ui;
+            }
+            myLs[src * 32 + lane] = es;
+            myLi[src * 32 + lane] = ei;
+            const float nthr = __shfl_sync(B200_FULL_MASK, es, kc - 1);
+            if (lane == src) rs.thr = nthr;
+            __syncwarp();
+        }
+    }
+}
+
+// One 32-column chunk of one accumulator row per thread: 3-input max tree against the row threshold (fast path,
+// ~0.6 instructions per score); the scan above runs only when some row of the warp has a hit.
+__device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int64_t pos0, const TcParams& p, float* myLs,
+                                              int* myLi, int lane, int kc, RowState& rs) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    const float g0 = max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), max3(v[6], v[7], v[8]));
+    const float g1 = max3(max3(v[9], v[10], v[11]), max3(v[12], v[13], v[14]), max3(v[15], v[16], v[17]));
+    const float g2 = max3(max3(v[18], v[19], v[20]), max3(v[21], v[22], v[23]), max3(v[24], v[25], v[26]));
+    const float g3 = max3(max3(v[27], v[28], v[29]), v[30], v[31]);
+    const float mx = fmaxf(max3(g0, g1, g2), g3);
+    if (__any_sync(B200_FULL_MASK, mx > rs.thr)) scan_chunk(v, pos0, p, myLs, myLi, lane, kc, rs);
+}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -200,56 +342,68 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) __trap();  // the CTA allocated all 512 columns, so its TMEM window starts at lane 0 / column 0
 
     const int n_work = p.n_row_tiles * p.n_splits;
 
     if (warp == 0) {
-        // ===================================================================== TMA producer (one lane)
-        if (lane == 0) {
-            uint32_t it = 0, work_it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
-                const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
-                const int t0 = split * p.tiles_per_split;
-                const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
-                if (work_it > 0) mbar_wait(bar_aempty, (work_it - 1) & 1);  // previous tile's MMAs are done with sA
+        // ===================================================================== TMA producer (converged warp, elected lane issues)
+        uint32_t stage = 0, ph = 0, work_it = 0;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
+            const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
+            if (work_it > 0) mbar_wait(bar_aempty, (work_it - 1) & 1);  // previous tile's MMAs are done with sA
+            if (elect_one()) {
                 mbar_arrive_expect_tx(bar_afull, (uint32_t)(S * KB * BLK_BYTES));
                 for (int s = 0; s < S; ++s)
                     for (int kb = 0; kb < KB; ++kb)
-                        tma_load_2d(smem_u32(sA + (size_t)(s * KB + kb) * BLK_BYTES), &tm_sub, bar_afull, kb * KBLK,
+                        tma_load_2d(sA_u + (uint32_t)(s * KB + kb) * BLK_BYTES, &tm_sub, bar_afull, kb * KBLK,
                                     (rt * S + s) * TILE_M);
-                for (int t = t0; t < t1; ++t) {
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const uint32_t stage = it % NS, ph = (it / NS) & 1;
-                        mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+            }
+            __syncwarp();
+            for (int t = t0; t < t1; ++t) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(bar_full + 8 * stage, BLK_BYTES);
-                        tma_load_2d(smem_u32(sB + (size_t)stage * BLK_BYTES), &tm_obj, bar_full + 8 * stage, kb * KBLK,
-                                    t * TILE_N);
+                        tma_load_2d(sB_u + stage * BLK_BYTES, &tm_obj, bar_full + 8 * stage, kb * KBLK, t * TILE_N);
+                    }
+                    __syncwarp();
+                    if (++stage == (uint32_t)NS) {
+                        stage = 0;
+                        ph ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer (one lane)
-        if (lane == 0) {
-            uint32_t it = 0, tile_it = 0, work_it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
-                const int split = w / p.n_row_tiles;
-                const int t0 = split * p.tiles_per_split;
-                const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
-                mbar_wait(bar_afull, work_it & 1);
+        // ===================================================================== MMA issuer
+        // The whole warp walks the loops converged and one elected lane issues: every operand of tcgen05.mma is then
+        // provably warp-uniform (loop counters, kernel parameters, the dynamic-smem base; TMEM base 0 because the CTA
+        // owns all 512 columns).  Issuing from inside an `if (lane == 0)` made the compiler wrap every UTCHMMA in an
+        // elect/broadcast retry loop that cost ~170 cycles per instruction (measured: tensor pipe 36 % busy).
+        uint32_t stage = 0, ph = 0, tile_it = 0, work_it = 0;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
+            const int split = w / p.n_row_tiles;
+            const int t0 = split * p.tiles_per_split;
+            const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
+            mbar_wait(bar_afull, work_it & 1);
+            tc_fence_after();
+            for (int t = t0; t < t1; ++t, ++tile_it) {
+                const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * buf, tph ^ 1);  // epilogue has drained this accumulator pair
                 tc_fence_after();
-                for (int t = t0; t < t1; ++t, ++tile_it) {
-                    const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
-                    mbar_wait(bar_tempty + 8 * buf, tph ^ 1);  // epilogue has drained this accumulator pair
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, ph);
                     tc_fence_after();
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const uint32_t stage = it % NS, ph = (it / NS) & 1;
-                        mbar_wait(bar_full + 8 * stage, ph);
-                        tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * BLK_BYTES));
+                    if (elect_one()) {
+                        const uint64_t bdesc = make_smem_desc(sB_u + stage * BLK_BYTES);
                         for (int s = 0; s < S; ++s) {
-                            const uint64_t adesc = make_smem_desc(smem_u32(sA + (size_t)(s * KB + kb) * BLK_BYTES));
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((buf * S + s) * TILE_N);
+                            const uint64_t adesc = make_smem_desc(sA_u + (uint32_t)(s * KB + kb) * BLK_BYTES);
+                            const uint32_t d_tmem = (uint32_t)((buf * S + s) * TILE_N);
 #pragma unroll
                             for (int k4 = 0; k4 < KBLK / UMMA_K; ++k4) {
                                 // +32 B per K step inside the 128 B swizzle atom = +2 in the (addr >> 4) field
@@ -258,11 +412,17 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                             }
                         }
                         umma_commit(bar_empty + 8 * stage);  // ring slot is free once these MMAs retire
+                        if (kb == KB - 1) umma_commit(bar_tfull + 8 * buf);  // accumulators of this tile are complete
                     }
-                    umma_commit(bar_tfull + 8 * buf);  // accumulators of this tile are complete
+                    __syncwarp();
+                    if (++stage == (uint32_t)NS) {
+                        stage = 0;
+                        ph ^= 1;
+                    }
                 }
-                umma_commit(bar_aempty);
             }
+            if (elect_one()) umma_commit(bar_aempty);
+            __syncwarp();
         }
     } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * S) {
         // ===================================================================== epilogue: select candidates
@@ -285,76 +445,53 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                 myLi[r * 32 + lane] = B200_PAD_ID;
             }
             __syncwarp();
-            float thr = row_ok ? -INFINITY : INFINITY;  // padded rows never produce candidates
-            int64_t flo = 0, fhi = 0;
-            if (row_ok && p.indptr) {
-                flo = p.indptr[grow];
-                fhi = p.indptr[grow + 1];
+            RowState rs;
+            rs.thr = row_ok ? -INFINITY : INFINITY;  // padded rows never produce candidates
+            rs.nv = B200_PAD_ID;
+            rs.cur = 0;
+            rs.fhi = 0;
+            if (row_ok && p.indptr && (int64_t)t0 * TILE_N < p.n_pos) {
+                // position the CSR cursor at the first object of this split (one lower_bound per work item)
+                const int64_t pos_first = (int64_t)t0 * TILE_N;
+                const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
+                int64_t lo = p.indptr[grow];
+                rs.fhi = p.indptr[grow + 1];
+                int64_t hi = rs.fhi;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (__ldg(p.indices + mid) < g_first)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                rs.cur = lo;
+                rs.nv = lo < rs.fhi ? __ldg(p.indices + lo) : B200_PAD_ID;
             }
             for (int t = t0; t < t1; ++t, ++tile_it) {
                 const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
                 mbar_wait(bar_tfull + 8 * buf, tph);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * S + s) * TILE_N);
+                const int64_t pos_t = (int64_t)t * TILE_N;
+                // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is scanned
+                uint32_t ra[32], rb[32];
+                tmem_ld_issue(tbase, ra);
 #pragma unroll 1
-                for (int cc = 0; cc < TILE_N / 32; ++cc) {
-                    float v[32];
-                    tmem_ld32(tbase + cc * 32, v);
-                    float m0 = max3(v[0], v[1], v[2]), m1 = max3(v[3], v[4], v[5]);
-                    float m2 = max3(v[6], v[7], v[8]), m3 = max3(v[9], v[10], v[11]);
-                    float m4 = max3(v[12], v[13], v[14]), m5 = max3(v[15], v[16], v[17]);
-                    float m6 = max3(v[18], v[19], v[20]), m7 = max3(v[21], v[22], v[23]);
-                    float m8 = max3(v[24], v[25], v[26]), m9 = max3(v[27], v[28], v[29]);
-                    m0 = max3(m0, m1, m2);
-                    m3 = max3(m3, m4, m5);
-                    m6 = max3(m6, m7, m8);
-                    m9 = max3(m9, v[30], v[31]);
-                    const float mx = fmaxf(max3(m0, m3, m6), m9);
-                    if (__any_sync(B200_FULL_MASK, mx > thr)) {
-                        // ---- slow path: some row of this warp has a score above its running threshold
-                        const int64_t pos0 = (int64_t)t * TILE_N + cc * 32;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            bool c = v[j] > thr;
-                            int obj = 0;
-                            if (c) {
-                                const int64_t pos = pos0 + j;
-                                c = pos < p.n_pos;
-                                if (c) {
-                                    obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
-                                    if (p.indptr) c = !csr_contains(p.indices, flo, fhi, obj + p.id_off);
-                                }
-                            }
-                            unsigned m = __ballot_sync(B200_FULL_MASK, c);
-                            while (m) {
-                                const int src = __ffs(m) - 1;
-                                m &= m - 1;
-                                const float cs = __shfl_sync(B200_FULL_MASK, v[j], src);
-                                const int ci = __shfl_sync(B200_FULL_MASK, obj, src);
-                                float es = myLs[src * 32 + lane];
-                                int ei = myLi[src * 32 + lane];
-                                const int ins = __popc(__ballot_sync(B200_FULL_MASK, es >= cs));
-                                const float us = __shfl_up_sync(B200_FULL_MASK, es, 1);
-                                const int ui = __shfl_up_sync(B200_FULL_MASK, ei, 1);
-                                if (lane == ins) {
-                                    es = cs;
-                                    ei = ci;
-                                } else if (lane > ins) {
-                                    es = us;
-                                    ei = ui;
-                                }
-                                myLs[src * 32 + lane] = es;
-                                myLi[src * 32 + lane] = ei;
-                                const float nthr = __shfl_sync(B200_FULL_MASK, es, kc - 1);
-                                if (lane == src) thr = nthr;
-                                __syncwarp();
-                            }
-                        }
+                for (int h = 0; h < 2; ++h) {  // two chunk pairs; not unrolled to keep the code I-cache resident
+                    tmem_ld_wait(ra);
+                    tmem_ld_issue(tbase + h * 64 + 32, rb);
+                    process_chunk(ra, pos_t + h * 64, p, myLs, myLi, lane, kc, rs);
+                    tmem_ld_wait(rb);
+                    if (h == 0) {
+                        tmem_ld_issue(tbase + 64, ra);
+                    } else {
+                        // every TMEM read of this tile has completed: hand the accumulator back before the last scan
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
                     }
+                    process_chunk(rb, pos_t + h * 64 + 32, p, myLs, myLi, lane, kc, rs);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             }
             // ---- write this warp's 32 candidate lists (coalesced 128 B rows)
             for (int r = 0; r < 32; ++r) {

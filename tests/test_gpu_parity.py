@@ -129,7 +129,7 @@ def test_golden_rankers(rb, case, force):
         atol = 2e-4 if dist == "euclidean" else 2e-6
         assert_same_ranking(fids, fscores, out[key + "|ids"], out[key + "|scores"], tie_tol=2e-6, atol=atol, msg=key)
         n_checked += 1
-    assert n_checked > 10
+    assert n_checked > 10 or (force == "tc" and case == 2)  # case 2 (64 objects) is below the tensor-core path's minimum
 
 
 def test_golden_puresvd_c1(rb, golden_dir):
