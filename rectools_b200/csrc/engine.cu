@@ -22,6 +22,7 @@
 #include "prep.cuh"
 #include "select.cuh"
 #include "tc_topk.cuh"
+#include "tc2_topk.cuh"
 
 namespace {
 
@@ -242,6 +243,32 @@ TcPlan plan_tc(int d_pad) {
     return pl;
 }
 
+// Shared-memory plan of the 2-SM kernel (per CTA: 128 subject rows, half of every object tile).
+TcPlan plan_tc2(int d_pad) {
+    TcPlan pl{};
+    pl.kblocks = d_pad / tc::KBLK;
+    pl.s_sub = 2;  // two candidate lists per row (one per column half)
+    const int a = pl.kblocks * tc::BLK_BYTES;
+    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 4;
+    const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
+    int stages = (tc::SMEM_LIMIT - fixed) / tc::BLK_BYTES;
+    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+    pl.ok = stages >= 2;
+    pl.n_stages = stages;
+    pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
+    return pl;
+}
+
+uint32_t make_idesc2(bool bf16) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= (bf16 ? 1u : 0u) << 7;
+    d |= (bf16 ? 1u : 0u) << 10;
+    d |= (uint32_t)(tc::TILE2_N >> 3) << 17;  // N = 256
+    d |= (uint32_t)(256 >> 4) << 24;          // M = 256 across the CTA pair
+    return d;
+}
+
 uint32_t make_idesc(bool bf16) {
     uint32_t d = 0;
     d |= 1u << 4;                       // accumulator format: F32
@@ -315,6 +342,9 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
             } else {
                 CK(cudaFuncSetAttribute(tc::tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
             }
+            TcPlan pl2 = plan_tc2(E->d_pad);
+            if (pl2.ok)
+                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
         }
         CK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     } catch (const CudaError& ce) {
@@ -550,6 +580,16 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
 
         // ---------------- path choice
         TcPlan pl = plan_tc(E->d_pad);
+        // 2-SM kernel (CTA pairs, cta_group::2) unless disabled or impossible; B200_TC_KERNEL=1 selects the 1-SM kernel
+        bool use_2sm = (E->sm_count % 2 == 0);
+        if (const char* env = getenv("B200_TC_KERNEL")) use_2sm = use_2sm && atoi(env) != 1;
+        if (use_2sm) {
+            TcPlan pl2 = plan_tc2(E->d_pad);
+            if (pl2.ok)
+                pl = pl2;
+            else
+                use_2sm = false;
+        }
         int k_cand = 0;
         if (k_out <= 10)
             k_cand = 16;
@@ -616,15 +656,18 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.n_rows = n_rows;
             tp.n_pos = n_pos;
             tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
-            tp.n_obj_tiles = (int)((n_pos + tc::TILE_N - 1) / tc::TILE_N);
+            const int tile_n = use_2sm ? tc::TILE2_N : tc::TILE_N;
+            const int lists_per_split = use_2sm ? 2 : 1;
+            tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
             // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
             int best_splits = 1;
             double best_eff = -1.0;
-            const int max_splits = std::max(1, std::min(16, tp.n_obj_tiles / 32));
+            const int max_splits = std::max(1, std::min(16, tp.n_obj_tiles * (tile_n / 128) / 32));
+            const int n_units = use_2sm ? E->sm_count / 2 : E->sm_count;  // CTAs or CTA pairs working concurrently
             for (int s = 1; s <= max_splits; ++s) {
                 const double work = (double)tp.n_row_tiles * s;
-                const double waves = std::ceil(work / E->sm_count);
-                const double eff = work / (waves * E->sm_count) - 0.01 * (s - 1);
+                const double waves = std::ceil(work / n_units);
+                const double eff = work / (waves * n_units) - 0.01 * (s - 1);
                 if (eff > best_eff + 1e-9) {
                     best_eff = eff;
                     best_splits = s;
@@ -636,23 +679,30 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             }
             tp.n_splits = best_splits;
             tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
-            tp.idesc = make_idesc(bf16);
+            tp.idesc = use_2sm ? make_idesc2(bf16) : make_idesc(bf16);
             tp.pos2obj = wl;
             tp.indptr = indptr;
             tp.indices = indices;
             tp.id_off = (int32_t)E->id_offset;
-            E->cand_scores.ensure(sizeof(float) * (size_t)best_splits * rows_pad * 32);
-            E->cand_ids.ensure(sizeof(int32_t) * (size_t)best_splits * rows_pad * 32);
-            E->cand_counts.ensure(sizeof(int32_t) * (size_t)best_splits * rows_pad);
+            const int n_lists = best_splits * lists_per_split;
+            E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * 32);
+            E->cand_ids.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad * 32);
+            E->cand_counts.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad);
             tp.cand_scores = E->cand_scores.as<float>();
             tp.cand_ids = E->cand_ids.as<int32_t>();
             tp.cand_counts = E->cand_counts.as<int32_t>();
             tp.rows_pad = rows_pad;
+            if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
             S.n_splits = best_splits;
             const int n_work = tp.n_row_tiles * tp.n_splits;
-            const int grid = std::min(n_work, E->sm_count);
             CK(cudaEventRecord(E->ev[2], st));
-            tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+            if (use_2sm) {
+                const int grid = 2 * std::min(n_work, n_units);
+                tc::tc2_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+            } else {
+                const int grid = std::min(n_work, n_units);
+                tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+            }
             CK(cudaGetLastError());
             CK(cudaEventRecord(E->ev[3], st));
             S.n_launches++;
@@ -665,7 +715,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             sp.in_scores = tp.cand_scores;
             sp.in_ids = tp.cand_ids;
             sp.in_counts = tp.cand_counts;
-            sp.n_lists = best_splits;
+            sp.n_lists = n_lists;
             sp.L = 32;
             sp.n_sel = n_rows;
             sp.list_stride_rows = rows_pad;

@@ -52,6 +52,7 @@ struct TcParams {
     int32_t* cand_ids;
     int32_t* cand_counts;     // [n_splits][rows_pad]
     int64_t rows_pad;
+    int32_t debug_mode;       // 0 = normal; 1 = no candidates (fast path only); 2 = epilogue skips the TMEM reads (measurement hooks)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -66,27 +67,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Wait for the phase with the given parity to complete.  A watchdog turns a protocol bug into a trap, not a hang.
+// Wait for the phase with the given parity to complete.  A watchdog turns a protocol bug into a trap, not a hang
+// (a failed try_wait already suspends the thread for a few hundred cycles, so 2^24 failures are seconds).
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (uint32_t spin = 0;; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if ((spin & 4095) == 4095) {
-            const long long now = clock64();
-            if (t0 == 0)
-                t0 = now;
-            else if (now - t0 > (1ll << 33))
-                __trap();
-        }
-    }
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 24)) __trap();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -124,13 +122,17 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, 128 x N x 16, issued by one thread.
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x N x 16, issued by one thread.  The two shared-memory matrix descriptors
+// differ only in their low word (start address >> 4); the high word (stride, version, swizzle) is shared.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                         uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accum)
         : "memory");
 }
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
@@ -164,16 +166,11 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
-// Shared-memory matrix descriptor: K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address  [0,14)
-    d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset [32,46)
-    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-    return d;
-}
+// Shared-memory matrix descriptor of a K-major operand block: 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart.
+//   lo: bits [0,14) start address >> 4, bits [16,30) leading byte offset >> 4 (unused for swizzled K-major: 0)
+//   hi: bits [0,14) stride byte offset >> 4 (1024 >> 4), bits [14,16) descriptor version 1 (sm_100), bits [29,32) layout 2
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return (saddr & 0x3FFFF) >> 4; }
+constexpr uint32_t SMEM_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
@@ -275,7 +272,7 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], int64_t pos0, c
             myLs[src * 32 + lane] = es;
             myLi[src * 32 + lane] = ei;
             const float nthr = __shfl_sync(B200_FULL_MASK, es, kc - 1);
-            if (lane == src) rs.thr = nthr;
+            if (lane == src) rs.thr = fmaxf(rs.thr, nthr);  // never loosen a bound borrowed from the row's other list
             __syncwarp();
         }
     }
@@ -385,7 +382,10 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
         // owns all 512 columns).  Issuing from inside an `if (lane == 0)` made the compiler wrap every UTCHMMA in an
         // elect/broadcast retry loop that cost ~170 cycles per instruction (measured: tensor pipe 36 % busy).
         uint32_t stage = 0, ph = 0, tile_it = 0, work_it = 0;
-        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
+        constexpr uint32_t BLK16 = BLK_BYTES >> 4;  // one 16 KiB block in descriptor address units
+        const uint32_t a_sub1 = (uint32_t)KB * BLK16;  // second sub-tile of the subject tile
+        const uint32_t idesc = p.idesc;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++work_it) {
             const int split = w / p.n_row_tiles;
             const int t0 = split * p.tiles_per_split;
@@ -396,25 +396,28 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                 const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * buf, tph ^ 1);  // epilogue has drained this accumulator pair
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
+                const uint32_t d0 = buf * (uint32_t)(S * TILE_N);
+                uint32_t a_lo = a_lo0;
+                for (int kb = 0; kb < KB; ++kb, a_lo += BLK16) {
                     mbar_wait(bar_full + 8 * stage, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t bdesc = make_smem_desc(sB_u + stage * BLK_BYTES);
-                        for (int s = 0; s < S; ++s) {
-                            const uint64_t adesc = make_smem_desc(sA_u + (uint32_t)(s * KB + kb) * BLK_BYTES);
-                            const uint32_t d_tmem = (uint32_t)((buf * S + s) * TILE_N);
-#pragma unroll
-                            for (int k4 = 0; k4 < KBLK / UMMA_K; ++k4) {
-                                // +32 B per K step inside the 128 B swizzle atom = +2 in the (addr >> 4) field
-                                umma_f16(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), p.idesc,
-                                         (uint32_t)((kb | k4) != 0));
-                            }
+                        const uint32_t b_lo = b_lo0 + stage * BLK16;
+                        // +32 B per K step inside the 128 B swizzle atom = +2 in descriptor address units
+                        umma_f16(d0, a_lo, b_lo, SMEM_DESC_HI, idesc, (uint32_t)(kb != 0));
+                        umma_f16(d0, a_lo + 2, b_lo + 2, SMEM_DESC_HI, idesc, 1u);
+                        umma_f16(d0, a_lo + 4, b_lo + 4, SMEM_DESC_HI, idesc, 1u);
+                        umma_f16(d0, a_lo + 6, b_lo + 6, SMEM_DESC_HI, idesc, 1u);
+                        if (S == 2) {
+                            const uint32_t d1 = d0 + TILE_N, a1 = a_lo + a_sub1;
+                            umma_f16(d1, a1, b_lo, SMEM_DESC_HI, idesc, (uint32_t)(kb != 0));
+                            umma_f16(d1, a1 + 2, b_lo + 2, SMEM_DESC_HI, idesc, 1u);
+                            umma_f16(d1, a1 + 4, b_lo + 4, SMEM_DESC_HI, idesc, 1u);
+                            umma_f16(d1, a1 + 6, b_lo + 6, SMEM_DESC_HI, idesc, 1u);
                         }
                         umma_commit(bar_empty + 8 * stage);  // ring slot is free once these MMAs retire
                         if (kb == KB - 1) umma_commit(bar_tfull + 8 * buf);  // accumulators of this tile are complete
                     }
-                    __syncwarp();
                     if (++stage == (uint32_t)NS) {
                         stage = 0;
                         ph ^= 1;
@@ -422,7 +425,6 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                 }
             }
             if (elect_one()) umma_commit(bar_aempty);
-            __syncwarp();
         }
     } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * S) {
         // ===================================================================== epilogue: select candidates
@@ -446,7 +448,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
             }
             __syncwarp();
             RowState rs;
-            rs.thr = row_ok ? -INFINITY : INFINITY;  // padded rows never produce candidates
+            rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;  // padded rows never produce candidates
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
@@ -474,6 +476,12 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * S + s) * TILE_N);
                 const int64_t pos_t = (int64_t)t * TILE_N;
                 // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c is scanned
+                if (p.debug_mode == 2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                    continue;
+                }
                 uint32_t ra[32], rb[32];
                 tmem_ld_issue(tbase, ra);
 #pragma unroll 1
