@@ -89,12 +89,12 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 // Row-major [rows, d_pad] 16-bit matrix, boxes of [128 rows x 64 cols] (128-byte rows, SWIZZLE_128B).
-bool make_tensor_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, bool is_bf16) {
+bool make_tensor_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, bool is_bf16, int box_rows = 128) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)b200::tc::KBLK, 128};
+    cuuint32_t box[2] = {(cuuint32_t)b200::tc::KBLK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -244,27 +244,28 @@ TcPlan plan_tc(int d_pad) {
 }
 
 // Shared-memory plan of the 2-SM kernel (per CTA: 128 subject rows, half of every object tile).
-TcPlan plan_tc2(int d_pad) {
+TcPlan plan_tc2(int d_pad, int tile_n) {
     TcPlan pl{};
     pl.kblocks = d_pad / tc::KBLK;
     pl.s_sub = 2;  // two candidate lists per row (one per column half)
     const int a = pl.kblocks * tc::BLK_BYTES;
-    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 4;
+    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8;
     const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
-    int stages = (tc::SMEM_LIMIT - fixed) / tc::BLK_BYTES;
+    const int blkb = tile_n / 2 * tc::KBLK * 2;  // object block bytes per CTA
+    int stages = (tc::SMEM_LIMIT - fixed) / blkb;
     if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
     pl.ok = stages >= 2;
     pl.n_stages = stages;
-    pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
+    pl.smem_bytes = fixed + stages * blkb;
     return pl;
 }
 
-uint32_t make_idesc2(bool bf16) {
+uint32_t make_idesc2(bool bf16, int tile_n) {
     uint32_t d = 0;
     d |= 1u << 4;
     d |= (bf16 ? 1u : 0u) << 7;
     d |= (bf16 ? 1u : 0u) << 10;
-    d |= (uint32_t)(tc::TILE2_N >> 3) << 17;  // N = 256
+    d |= (uint32_t)(tile_n >> 3) << 17;
     d |= (uint32_t)(256 >> 4) << 24;          // M = 256 across the CTA pair
     return d;
 }
@@ -342,9 +343,15 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
             } else {
                 CK(cudaFuncSetAttribute(tc::tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
             }
-            TcPlan pl2 = plan_tc2(E->d_pad);
-            if (pl2.ok)
-                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
+            TcPlan pl2 = plan_tc2(E->d_pad, 256), pl2b = plan_tc2(E->d_pad, 128);
+            if (pl2.ok) {
+                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
+            }
+            if (pl2b.ok) {
+                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2b.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2b.smem_bytes));
+            }
         }
         CK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     } catch (const CudaError& ce) {
@@ -583,8 +590,11 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         // 2-SM kernel (CTA pairs, cta_group::2) unless disabled or impossible; B200_TC_KERNEL=1 selects the 1-SM kernel
         bool use_2sm = (E->sm_count % 2 == 0);
         if (const char* env = getenv("B200_TC_KERNEL")) use_2sm = use_2sm && atoi(env) != 1;
+        // tile width of the 2-SM kernel: 256 objects x 2 TMEM buffers (default) or 128 x 4 (B200_TC_TILE=128)
+        int tile2_n = 256;
+        if (const char* env = getenv("B200_TC_TILE")) tile2_n = atoi(env) == 128 ? 128 : 256;
         if (use_2sm) {
-            TcPlan pl2 = plan_tc2(E->d_pad);
+            TcPlan pl2 = plan_tc2(E->d_pad, tile2_n);
             if (pl2.ok)
                 pl = pl2;
             else
@@ -632,7 +642,9 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                 S.n_launches++;
             }
             // objects: resident 16-bit copy, or a whitelist gather of it
-            CUtensorMap tm_obj = E->tm_obj_full;
+            const int obj_box_rows = use_2sm ? tile2_n / 2 : 128;  // object rows one CTA loads per ring block
+            const void* obj_base = E->obj16.p;
+            int64_t obj_rows = E->n_obj_pad;
             if (wl) {
                 const int64_t npad = round_up(n_pos, tc::TILE_N);
                 E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
@@ -641,9 +653,12 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                                                                                  E->obj16_wl.as<uint4>());
                 CK(cudaGetLastError());
                 S.n_launches++;
-                if (!make_tensor_map(&tm_obj, E->obj16_wl.p, npad, E->d_pad, bf16))
-                    return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (whitelist objects)");
+                obj_base = E->obj16_wl.p;
+                obj_rows = npad;
             }
+            CUtensorMap tm_obj;
+            if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16, obj_box_rows))
+                return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (objects)");
             CUtensorMap tm_sub;
             if (!make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
                 return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (subjects)");
@@ -656,7 +671,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.n_rows = n_rows;
             tp.n_pos = n_pos;
             tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
-            const int tile_n = use_2sm ? tc::TILE2_N : tc::TILE_N;
+            const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
             const int lists_per_split = use_2sm ? 2 : 1;
             tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
             // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
@@ -679,7 +694,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             }
             tp.n_splits = best_splits;
             tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
-            tp.idesc = use_2sm ? make_idesc2(bf16) : make_idesc(bf16);
+            tp.idesc = use_2sm ? make_idesc2(bf16, tile2_n) : make_idesc(bf16);
             tp.pos2obj = wl;
             tp.indptr = indptr;
             tp.indices = indices;
@@ -698,7 +713,16 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             CK(cudaEventRecord(E->ev[2], st));
             if (use_2sm) {
                 const int grid = 2 * std::min(n_work, n_units);
-                tc::tc2_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
+                if (const char* env = getenv("B200_TC_STAGE")) stage_regs = atoi(env) != 0;
+                if (tile2_n == 256 && stage_regs)
+                    tc::tc2_topk_kernel<256, 2, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                else if (tile2_n == 256)
+                    tc::tc2_topk_kernel<256, 2, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                else if (stage_regs)
+                    tc::tc2_topk_kernel<128, 4, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                else
+                    tc::tc2_topk_kernel<128, 4, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
             } else {
                 const int grid = std::min(n_work, n_units);
                 tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);

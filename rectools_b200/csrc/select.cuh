@@ -262,8 +262,12 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectPara
         }
         if (RESCORE) {
             // certificate bookkeeping on the approximate scores
-            const float a = valid ? p.in_scores[o] : -INFINITY;
-            if (valid && e == p.k_cand - 1) {
+            // (lists are unsorted and L == 32: one list per 32-lane chunk; a full list's smallest approximate score
+            // bounds everything that list ever discarded)
+            float a = valid ? p.in_scores[o] : INFINITY;
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) a = fminf(a, __shfl_xor_sync(B200_FULL_MASK, a, sh));
+            if (cnt >= p.k_cand) {
                 any_full = true;
                 thr_approx = fmaxf(thr_approx, a);
             }

@@ -22,7 +22,6 @@
 namespace b200 {
 namespace tc {
 
-constexpr int TILE2_N = 256;  // objects per tile of the CTA pair (128 loaded by each CTA)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -77,25 +76,45 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                  : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// TN   = objects per tile of the CTA pair (each CTA loads TN/2 of them and owns TN accumulator columns per buffer)
+// NBUF = accumulator buffers in TMEM (NBUF * TN = 512 columns): 2 x 256 minimises MMA instructions and shared-memory
+//        operand traffic (64 B/clk per CTA), 4 x 128 (96 B/clk) lets the MMA run up to three tiles ahead of a warp
+//        that is busy inserting candidates.
+// STAGE = true: an epilogue warp first copies its whole [32 rows x TN/2 columns] slice of the accumulator to registers
+//        (one wide tcgen05.ld), hands the TMEM buffer back at once and only then scans the scores, so the MMA of tile
+//        t+2 never waits for candidate insertion of tile t (352 threads per CTA to afford ~180 registers per thread).
+template <bool STAGE>
+struct Tc2Threads {
+    static constexpr int EPI0 = STAGE ? 3 : EPI_WARP0;  // first epilogue warp; (warp & 3) is its TMEM lane quarter
+    static constexpr int THREADS = (EPI0 + 8) * 32;
+};
+
+template <int TN, int NBUF, bool STAGE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Threads<STAGE>::THREADS, 1)
 tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant__ CUtensorMap tm_obj, const TcParams p) {
+    static_assert(TN * NBUF == TMEM_COLS && (TN == 256 || TN == 128), "accumulators must fill the 512 TMEM columns");
+    constexpr int TILE2_N = TN;
+    constexpr int HALF_N = TN / 2;                 // object rows per CTA and tile = accumulator columns per epilogue warp
+    constexpr int BLKB_BYTES = HALF_N * KBLK * 2;  // one object ring block: [TN/2 rows][128 B]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
     const int KB = p.kblocks, NS = p.n_stages;
     uint8_t* sA = smem;                                      // [KB] blocks: this CTA's 128 subject rows
     uint8_t* sB = sA + (size_t)KB * BLK_BYTES;               // [NS] blocks: this CTA's half of the object tiles
-    float* sLs = reinterpret_cast<float*>(sB + (size_t)NS * BLK_BYTES);  // [2 halves][128 rows][32] candidate scores
+    float* sLs = reinterpret_cast<float*>(sB + (size_t)NS * BLKB_BYTES);  // [2 halves][128 rows][32] candidate scores
     int* sLi = reinterpret_cast<int*>(sLs + 2 * TILE_M * 32);            // [2][128][32] candidate ids
-    float* sThr = reinterpret_cast<float*>(sLi + 2 * TILE_M * 32);       // [2][128] published thresholds
+    // [2][128] published (threshold, work-item tag) pairs: the tag keeps a warp that has already moved on to the next
+    // subject tile from adopting its partner's threshold of the previous one
+    unsigned long long* sThr = reinterpret_cast<unsigned long long*>(sLi + 2 * TILE_M * 32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sThr + 2 * TILE_M);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES);
     const uint32_t bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 1);
     const uint32_t bar_tfull = smem_u32(bars + 2 * MAX_STAGES + 2);
-    const uint32_t bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 4);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+    const uint32_t bar_tempty = smem_u32(bars + 2 * MAX_STAGES + 2 + NBUF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 + 2 * NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader
@@ -108,7 +127,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
         }
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
             mbar_init(bar_tempty + 8 * b, 16);  // 8 epilogue warps in each of the two CTAs arrive on the leader's copy
         }
@@ -116,6 +135,8 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
         tma_prefetch_desc(&tm_sub);
         tma_prefetch_desc(&tm_obj);
     }
+    constexpr int EPI0 = Tc2Threads<STAGE>::EPI0;
+    if (warp >= EPI0) sThr[(warp - EPI0) * 32 + lane] = ~0ull;  // tag no work item can carry
     if (warp == 2) {
         tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
         tmem_relinquish_2sm();
@@ -127,43 +148,42 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
     if (tmem_base != 0) __trap();  // all 512 columns are ours
 
     const int n_work = p.n_row_tiles * p.n_splits;
-    constexpr uint32_t BLK16 = BLK_BYTES >> 4;
+    constexpr uint32_t BLK16 = BLK_BYTES >> 4;    // subject block in descriptor address units
+    constexpr uint32_t BLKB16 = BLKB_BYTES >> 4;  // object block
 
     if (warp == 0) {
-        // ===================================================================== TMA producer (both CTAs)
-        uint32_t stage = 0, ph = 0, work_it = 0;
-        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-        for (int w = pair; w < n_work; w += n_pairs, ++work_it) {
-            const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
-            const int t0 = split * p.tiles_per_split;
-            const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
-            if (work_it > 0) mbar_wait(bar_aempty, (work_it - 1) & 1);
-            if (elect_one()) {
+        // ===================================================================== TMA producer (both CTAs, one elected thread)
+        if (elect_one()) {
+            uint32_t stage = 0, ph = 0, work_it = 0;
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            for (int w = pair; w < n_work; w += n_pairs, ++work_it) {
+                const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
+                const int t0 = split * p.tiles_per_split;
+                const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
+                if (work_it > 0) mbar_wait(bar_aempty, (work_it - 1) & 1);
                 if (rank == 0) mbar_arrive_expect_tx(bar_afull, (uint32_t)(2 * KB * BLK_BYTES));
                 for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d_2sm(sA_u + (uint32_t)kb * BLK_BYTES, &tm_sub, bar_afull, kb * KBLK,
-                                    (rt * 2 + (int)rank) * TILE_M);
-            }
-            __syncwarp();
-            for (int t = t0; t < t1; ++t) {
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, ph ^ 1);
-                    if (elect_one()) {
-                        if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * BLK_BYTES);
-                        tma_load_2d_2sm(sB_u + stage * BLK_BYTES, &tm_obj, bar_full + 8 * stage, kb * KBLK,
-                                        t * TILE2_N + (int)rank * TILE_M);
-                    }
-                    __syncwarp();
-                    if (++stage == (uint32_t)NS) {
-                        stage = 0;
-                        ph ^= 1;
+                    tma_load_2d_2sm(sA_u + (uint32_t)kb * BLK_BYTES, &tm_sub, bar_afull, kb * KBLK, (rt * 2 + (int)rank) * TILE_M);
+                for (int t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                        if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * BLKB_BYTES);
+                        tma_load_2d_2sm(sB_u + stage * BLKB_BYTES, &tm_obj, bar_full + 8 * stage, kb * KBLK,
+                                        t * TILE2_N + (int)rank * HALF_N);
+                        if (++stage == (uint32_t)NS) {
+                            stage = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (leader CTA only)
-        if (rank == 0) {
+        // One elected thread runs the whole role (waits included): measured with per-k-block election the issue loop cost
+        // ~315 cycles per 4 MMAs (256 cycles of tensor work) and the tensor pipe sat at 45 %.
+        if (rank == 0 && elect_one()) {
             uint32_t stage = 0, ph = 0, tile_it = 0, work_it = 0;
             const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
             const uint32_t idesc = p.idesc;
@@ -174,7 +194,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                 mbar_wait(bar_afull, work_it & 1);
                 tc_fence_after();
                 for (int t = t0; t < t1; ++t, ++tile_it) {
-                    const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
+                    const uint32_t buf = tile_it % NBUF, tph = (tile_it / NBUF) & 1;
                     mbar_wait(bar_tempty + 8 * buf, tph ^ 1);  // both CTAs' epilogues have drained this accumulator
                     tc_fence_after();
                     const uint32_t d0 = buf * (uint32_t)TILE2_N;
@@ -182,54 +202,52 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                     for (int kb = 0; kb < KB; ++kb, a_lo += BLK16) {
                         mbar_wait(bar_full + 8 * stage, ph);
                         tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t b_lo = b_lo0 + stage * BLK16;
-                            umma_f16_2sm(d0, a_lo, b_lo, SMEM_DESC_HI, idesc, (uint32_t)(kb != 0));
-                            umma_f16_2sm(d0, a_lo + 2, b_lo + 2, SMEM_DESC_HI, idesc, 1u);
-                            umma_f16_2sm(d0, a_lo + 4, b_lo + 4, SMEM_DESC_HI, idesc, 1u);
-                            umma_f16_2sm(d0, a_lo + 6, b_lo + 6, SMEM_DESC_HI, idesc, 1u);
-                            umma_commit_2sm(bar_empty + 8 * stage);  // frees this ring slot in both CTAs
-                            if (kb == KB - 1) umma_commit_2sm(bar_tfull + 8 * buf);
-                        }
+                        const uint32_t b_lo = b_lo0 + stage * BLKB16;
+                        umma_f16_2sm(d0, a_lo, b_lo, SMEM_DESC_HI, idesc, (uint32_t)(kb != 0));
+                        umma_f16_2sm(d0, a_lo + 2, b_lo + 2, SMEM_DESC_HI, idesc, 1u);
+                        umma_f16_2sm(d0, a_lo + 4, b_lo + 4, SMEM_DESC_HI, idesc, 1u);
+                        umma_f16_2sm(d0, a_lo + 6, b_lo + 6, SMEM_DESC_HI, idesc, 1u);
+                        umma_commit_2sm(bar_empty + 8 * stage);  // frees this ring slot in both CTAs
                         if (++stage == (uint32_t)NS) {
                             stage = 0;
                             ph ^= 1;
                         }
                     }
+                    umma_commit_2sm(bar_tfull + 8 * buf);
                 }
-                if (elect_one()) umma_commit_2sm(bar_aempty);
+                umma_commit_2sm(bar_aempty);
             }
         }
-    } else if (warp >= EPI_WARP0) {
+        __syncwarp();
+    } else if (warp >= EPI0) {
         // ===================================================================== epilogue (both CTAs): select candidates
-        const int ew = warp - EPI_WARP0;
-        const int half = ew >> 2, quarter = ew & 3;  // column half of the tile / TMEM lane quarter (== warp % 4)
+        const int ew = warp - EPI0;
+        const int half = ew >> 2, quarter = warp & 3;  // column half of the tile / TMEM lane quarter (== warp % 4)
         const int wrow0 = quarter * 32;              // first CTA-local subject row of this warp
-        float* myLs = sLs + (size_t)(half * TILE_M + wrow0) * 32;
-        int* myLi = sLi + (size_t)(half * TILE_M + wrow0) * 32;
-        float* myThr = sThr + half * TILE_M + wrow0 + lane;
-        const float* peerThr = sThr + (half ^ 1) * TILE_M + wrow0 + lane;
+        const uint32_t ls = smem_u32(sLs + (size_t)(half * TILE_M + wrow0) * 32) + lane * 4;  // [slot][lane] arrays of this warp
+        const uint32_t li = smem_u32(sLi + (size_t)(half * TILE_M + wrow0) * 32) + lane * 4;
+        volatile unsigned long long* myThr = sThr + half * TILE_M + wrow0 + lane;
+        const volatile unsigned long long* peerThr = sThr + (half ^ 1) * TILE_M + wrow0 + lane;
+        uint32_t work_tag = 0;
         const int kc = p.k_cand;
         uint32_t tile_it = 0;
-        for (int w = pair; w < n_work; w += n_pairs) {
+        for (int w = pair; w < n_work; w += n_pairs, ++work_tag) {
             const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
             const int64_t grow0 = ((int64_t)rt * 2 + rank) * TILE_M + wrow0;  // global row of lane 0
             const int64_t grow = grow0 + lane;
             const bool row_ok = grow < p.n_rows;
-            for (int r = 0; r < 32; ++r) {
-                myLs[r * 32 + lane] = -INFINITY;
-                myLi[r * 32 + lane] = B200_PAD_ID;
-            }
             RowState rs;
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;
+            rs.cnt = 0;
+            rs.minpos = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
-            *myThr = rs.thr;
+            *myThr = ((unsigned long long)work_tag << 32) | __float_as_uint(rs.thr);
             __syncwarp();
-            const int64_t pos_first = (int64_t)t0 * TILE2_N + half * 128;
+            const int64_t pos_first = (int64_t)t0 * TILE2_N + half * HALF_N;
             if (row_ok && p.indptr && pos_first < p.n_pos) {
                 const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
                 int64_t lo = p.indptr[grow];
@@ -246,53 +264,69 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                 rs.nv = lo < rs.fhi ? __ldg(p.indices + lo) : B200_PAD_ID;
             }
             for (int t = t0; t < t1; ++t, ++tile_it) {
-                const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;
+                const uint32_t buf = tile_it % NBUF, tph = (tile_it / NBUF) & 1;
                 // exchange thresholds with the thread that owns the other column half of this row (monotone, racy by
                 // design: a stale value is only a weaker bound)
-                *myThr = rs.thr;
-                rs.thr = fmaxf(rs.thr, *reinterpret_cast<const volatile float*>(peerThr));
+                *myThr = ((unsigned long long)work_tag << 32) | __float_as_uint(rs.thr);
+                {
+                    const unsigned long long pv = *peerThr;
+                    if ((uint32_t)(pv >> 32) == work_tag) rs.thr = fmaxf(rs.thr, __uint_as_float((uint32_t)pv));
+                }
                 mbar_wait(bar_tfull + 8 * buf, tph);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TILE2_N + half * 128);
-                const int64_t pos_t = (int64_t)t * TILE2_N + half * 128;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TILE2_N + half * HALF_N);
+                const int64_t pos_t = (int64_t)t * TILE2_N + half * HALF_N;
                 if (p.debug_mode == 2) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
                     continue;
                 }
-                uint32_t ra[32], rb[32];
-                tmem_ld_issue(tbase, ra);
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    tmem_ld_wait(ra);
-                    tmem_ld_issue(tbase + h * 64 + 32, rb);
-                    process_chunk(ra, pos_t + h * 64, p, myLs, myLi, lane, kc, rs);
-                    tmem_ld_wait(rb);
-                    if (h == 0) {
-                        tmem_ld_issue(tbase + 64, ra);
-                    } else {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+                if constexpr (STAGE) {
+                    uint32_t r[HALF_N];
+                    if constexpr (HALF_N == 128)
+                        tmem_ld128_sync(tbase, r);
+                    else
+                        tmem_ld64_sync(tbase, r);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);  // accumulator free again
+                    process_chunk<0, HALF_N>(r, pos_t, p, ls, li, kc, rs);
+                    process_chunk<32, HALF_N>(r, pos_t + 32, p, ls, li, kc, rs);
+                    if constexpr (HALF_N == 128) {
+                        process_chunk<64, HALF_N>(r, pos_t + 64, p, ls, li, kc, rs);
+                        process_chunk<96, HALF_N>(r, pos_t + 96, p, ls, li, kc, rs);
                     }
-                    process_chunk(rb, pos_t + h * 64 + 32, p, myLs, myLi, lane, kc, rs);
+                } else {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_issue(tbase, ra);
+#pragma unroll 1
+                    for (int h = 0; h < HALF_N / 64; ++h) {
+                        tmem_ld_wait(ra);
+                        tmem_ld_issue(tbase + h * 64 + 32, rb);
+                        process_chunk(ra, pos_t + h * 64, p, ls, li, kc, rs);
+                        tmem_ld_wait(rb);
+                        if (h + 1 < HALF_N / 64) {
+                            tmem_ld_issue(tbase + (h + 1) * 64, ra);
+                        } else {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);
+                        }
+                        process_chunk(rb, pos_t + h * 64 + 32, p, ls, li, kc, rs);
+                    }
                 }
             }
-            // ---- write this warp's 32 candidate lists: list index = split * 2 + column half
-            for (int r = 0; r < 32; ++r) {
-                const int64_t gr = grow0 + r;
-                if (gr >= p.n_rows) break;
-                const float es = myLs[r * 32 + lane];
-                const int ei = myLi[r * 32 + lane];
-                const int64_t li = (int64_t)(split * 2 + half) * p.rows_pad + gr;
-                const bool keep = lane < kc;
-                p.cand_scores[li * 32 + lane] = keep ? es : -INFINITY;
-                p.cand_ids[li * 32 + lane] = keep ? ei : B200_PAD_ID;
-                const int cnt = __popc(__ballot_sync(B200_FULL_MASK, keep && ei != B200_PAD_ID));
-                if (lane == 0) p.cand_counts[li] = cnt;
+            // ---- write this thread's candidate list (unsorted): list index = split * 2 + column half
+            if (row_ok) {
+                const int64_t lrow = (int64_t)(split * 2 + half) * p.rows_pad + grow;
+                for (int e = 0; e < 32; ++e) {
+                    const bool keep = e < rs.cnt;
+                    p.cand_scores[lrow * 32 + e] = keep ? lds_f32(ls + e * 128) : -INFINITY;
+                    p.cand_ids[lrow * 32 + e] = keep ? lds_s32(li + e * 128) : B200_PAD_ID;
+                }
+                p.cand_counts[lrow] = rs.cnt;
             }
-            __syncwarp();
         }
     }
 

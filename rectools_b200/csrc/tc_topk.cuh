@@ -166,6 +166,41 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 
+// Synchronous wide TMEM reads (load + wait in one asm statement so that no use can be scheduled in between):
+// thread i of the warp gets TMEM lane (base_lane + i), 64 / 128 consecutive fp32 columns.
+#define B200_R8(a, n) "=r"(a[n]), "=r"(a[n + 1]), "=r"(a[n + 2]), "=r"(a[n + 3]), "=r"(a[n + 4]), "=r"(a[n + 5]), "=r"(a[n + 6]), "=r"(a[n + 7])
+__device__ __forceinline__ void tmem_ld64_sync(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : B200_R8(r, 0), B200_R8(r, 8), B200_R8(r, 16), B200_R8(r, 24), B200_R8(r, 32), B200_R8(r, 40), B200_R8(r, 48),
+          B200_R8(r, 56)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld128_sync(uint32_t taddr, uint32_t (&r)[128]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x128.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, "
+        "%64, %65, %66, %67, %68, %69, %70, %71, %72, %73, %74, %75, %76, %77, %78, %79, "
+        "%80, %81, %82, %83, %84, %85, %86, %87, %88, %89, %90, %91, %92, %93, %94, %95, "
+        "%96, %97, %98, %99, %100, %101, %102, %103, %104, %105, %106, %107, %108, %109, %110, %111, "
+        "%112, %113, %114, %115, %116, %117, %118, %119, %120, %121, %122, %123, %124, %125, %126, %127}, [%128];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : B200_R8(r, 0), B200_R8(r, 8), B200_R8(r, 16), B200_R8(r, 24), B200_R8(r, 32), B200_R8(r, 40), B200_R8(r, 48),
+          B200_R8(r, 56), B200_R8(r, 64), B200_R8(r, 72), B200_R8(r, 80), B200_R8(r, 88), B200_R8(r, 96), B200_R8(r, 104),
+          B200_R8(r, 112), B200_R8(r, 120)
+        : "r"(taddr)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor of a K-major operand block: 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart.
 //   lo: bits [0,14) start address >> 4, bits [16,30) leading byte offset >> 4 (unused for swizzled K-major: 0)
 //   hi: bits [0,14) stride byte offset >> 4 (1024 >> 4), bits [14,16) descriptor version 1 (sm_100), bits [29,32) layout 2
@@ -177,11 +212,50 @@ __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(
 // ------------------------------------------------------------------------------------------------ epilogue helpers
 // Per-row state of the streaming selection (registers of the thread that owns the row).
 struct RowState {
-    float thr;    // K'-th best approximate score so far (-inf until the list is full, +inf for padded rows)
+    float thr;    // smallest score of the row's candidate list once it holds K' entries (-inf before, +inf: padded row)
+    int cnt;      // entries in the list (<= K')
+    int minpos;   // slot of the smallest entry once the list is full
     int nv;       // next viewed global object id >= the stream position (B200_PAD_ID when the CSR row is exhausted)
     int64_t cur;  // index of `nv` in csr indices
     int64_t fhi;  // end of the row's CSR slice
 };
+
+// Candidate lists live in shared memory as [slot][lane]: the thread that owns a row reads and writes only its own
+// column (bank = lane, conflict-free), so all 32 rows of a warp can take candidates at the same time.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Keep the K' best (score, id) pairs of a row: append while the list is short, afterwards overwrite the current
+// minimum and re-scan for the new one (K' independent shared-memory loads; runs for all rows of the warp in parallel).
+// ls / li = shared addresses of slot 0 of this thread's column in the score / id arrays.
+__device__ __forceinline__ void list_insert(uint32_t ls, uint32_t li, int kc, RowState& rs, float val, int obj) {
+    const int slot = rs.cnt < kc ? rs.cnt : rs.minpos;
+    sts_f32(ls + slot * 128, val);
+    sts_s32(li + slot * 128, obj);
+    if (rs.cnt < kc && ++rs.cnt < kc) return;
+    float mn = INFINITY;
+    int mp = 0;
+#pragma unroll 8
+    for (int e = 0; e < kc; ++e) {
+        const float x = lds_f32(ls + e * 128);
+        if (x < mn) {
+            mn = x;
+            mp = e;
+        }
+    }
+    rs.minpos = mp;
+    rs.thr = fmaxf(rs.thr, mn);  // never loosen a bound borrowed from the row's other list
+}
 
 // Objects are visited in ascending id order, so the filter_pairs_csr lookup is a merge, not a search: `nv` trails
 // the stream and is advanced only when a candidate reaches it (two linear steps, then lower_bound on the rest).
@@ -224,73 +298,58 @@ __device__ __forceinline__ float select32(const float (&v)[32], int j) {
 }
 
 // Slow path of one chunk (compact on purpose: the unrolled per-column version thrashed the instruction cache).
-// Every lane builds the bit mask of its columns above the row threshold, then the warp drains the masks: each lane
-// takes its lowest pending column (ascending object order per row, as the CSR cursor needs), re-checks it against
-// the possibly raised threshold, drops padded / viewed objects, and the survivors are inserted one by one into
-// their row's sorted candidate list (warp-cooperative: one list entry per lane).
-__device__ __forceinline__ void scan_chunk(const float (&v)[32], int64_t pos0, const TcParams& p, float* myLs, int* myLi,
-                                        int lane, int kc, RowState& rs) {
-    unsigned hits = 0;
+// Every lane builds the bit mask of its columns above the row threshold and then drains it: lowest pending column
+// first, re-checked against the possibly raised threshold, padded / viewed objects dropped, survivors inserted
+// into the row's candidate list by the thread that owns the row.
+template <int J0, int J1>
+__device__ __forceinline__ unsigned hit_mask(const float (&v)[32], float thr) {
+    unsigned m = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) hits |= (v[j] > rs.thr) ? (1u << j) : 0u;
+    for (int j = J0; j < J1; ++j) m |= (v[j] > thr) ? (1u << j) : 0u;
+    return m;
+}
+
+__device__ __forceinline__ void scan_chunk(const float (&v)[32], float g0, float g1, float g2, float g3, int64_t pos0,
+                                           const TcParams& p, uint32_t ls, uint32_t li, int kc, RowState& rs) {
+    // per-lane bit mask of the columns above the row threshold, built only for the column groups whose maximum
+    // (already known from the fast path) shows a hit somewhere in the warp
+    unsigned hits = 0;
+    if (__any_sync(B200_FULL_MASK, g0 > rs.thr)) hits |= hit_mask<0, 9>(v, rs.thr);
+    if (__any_sync(B200_FULL_MASK, g1 > rs.thr)) hits |= hit_mask<9, 18>(v, rs.thr);
+    if (__any_sync(B200_FULL_MASK, g2 > rs.thr)) hits |= hit_mask<18, 27>(v, rs.thr);
+    if (__any_sync(B200_FULL_MASK, g3 > rs.thr)) hits |= hit_mask<27, 32>(v, rs.thr);
+    // drain: every thread works through its own columns in ascending object order (what the CSR cursor needs);
+    // rows are independent, so all lanes insert concurrently
     while (__any_sync(B200_FULL_MASK, hits != 0)) {
-        bool c = false;
-        float val = 0.f;
-        int obj = 0;
         if (hits) {
             const int j = __ffs(hits) - 1;
             hits &= hits - 1;
-            val = select32(v, j);
-            c = val > rs.thr;
-            if (c) {
+            const float val = select32(v, j);
+            if (val > rs.thr) {  // the threshold may have risen since the mask was built
                 const int64_t pos = pos0 + j;
-                c = pos < p.n_pos;
-                if (c) {
-                    obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
-                    c = !csr_is_viewed(p.indices, rs, obj + p.id_off);
+                if (pos < p.n_pos) {
+                    const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
+                    if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
                 }
             }
-        }
-        unsigned m = __ballot_sync(B200_FULL_MASK, c);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float cs = __shfl_sync(B200_FULL_MASK, val, src);
-            const int ci = __shfl_sync(B200_FULL_MASK, obj, src);
-            float es = myLs[src * 32 + lane];
-            int ei = myLi[src * 32 + lane];
-            const int ins = __popc(__ballot_sync(B200_FULL_MASK, es >= cs));
-            const float us = __shfl_up_sync(B200_FULL_MASK, es, 1);
-            const int ui = __shfl_up_sync(B200_FULL_MASK, ei, 1);
-            if (lane == ins) {
-                es = cs;
-                ei = ci;
-            } else if (lane > ins) {
-                es = us;
-                ei = ui;
-            }
-            myLs[src * 32 + lane] = es;
-            myLi[src * 32 + lane] = ei;
-            const float nthr = __shfl_sync(B200_FULL_MASK, es, kc - 1);
-            if (lane == src) rs.thr = fmaxf(rs.thr, nthr);  // never loosen a bound borrowed from the row's other list
-            __syncwarp();
         }
     }
 }
 
 // One 32-column chunk of one accumulator row per thread: 3-input max tree against the row threshold (fast path,
 // ~0.6 instructions per score); the scan above runs only when some row of the warp has a hit.
-__device__ __forceinline__ void process_chunk(const uint32_t (&r)[32], int64_t pos0, const TcParams& p, float* myLs,
-                                              int* myLi, int lane, int kc, RowState& rs) {
+template <int OFF = 0, int NREG = 32>
+__device__ __forceinline__ void process_chunk(const uint32_t (&r)[NREG], int64_t pos0, const TcParams& p, uint32_t ls,
+                                              uint32_t li, int kc, RowState& rs) {
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[OFF + i]);
     const float g0 = max3(max3(v[0], v[1], v[2]), max3(v[3], v[4], v[5]), max3(v[6], v[7], v[8]));
     const float g1 = max3(max3(v[9], v[10], v[11]), max3(v[12], v[13], v[14]), max3(v[15], v[16], v[17]));
     const float g2 = max3(max3(v[18], v[19], v[20]), max3(v[21], v[22], v[23]), max3(v[24], v[25], v[26]));
     const float g3 = max3(max3(v[27], v[28], v[29]), v[30], v[31]);
     const float mx = fmaxf(max3(g0, g1, g2), g3);
-    if (__any_sync(B200_FULL_MASK, mx > rs.thr)) scan_chunk(v, pos0, p, myLs, myLi, lane, kc, rs);
+    if (__any_sync(B200_FULL_MASK, mx > rs.thr)) scan_chunk(v, g0, g1, g2, g3, pos0, p, ls, li, kc, rs);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -431,8 +490,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
         const int ew = warp - EPI_WARP0;
         const int s = ew >> 2, quarter = ew & 3;  // quarter == warp % 4: the TMEM lanes this warp may read
         const int wrow0 = s * TILE_M + quarter * 32;  // first CTA-local row of this warp
-        float* myLs = sLs + (size_t)wrow0 * 32;
-        int* myLi = sLi + (size_t)wrow0 * 32;
+        const uint32_t ls = smem_u32(sLs + (size_t)wrow0 * 32) + lane * 4;  // [slot][lane] arrays of this warp
+        const uint32_t li = smem_u32(sLi + (size_t)wrow0 * 32) + lane * 4;
         const int kc = p.k_cand;
         uint32_t tile_it = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -442,13 +501,10 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
             const int64_t grow0 = (int64_t)rt * S * TILE_M + wrow0;  // global row of lane 0
             const int64_t grow = grow0 + lane;
             const bool row_ok = grow < p.n_rows;
-            for (int r = 0; r < 32; ++r) {
-                myLs[r * 32 + lane] = -INFINITY;
-                myLi[r * 32 + lane] = B200_PAD_ID;
-            }
-            __syncwarp();
             RowState rs;
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;  // padded rows never produce candidates
+            rs.cnt = 0;
+            rs.minpos = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
@@ -488,7 +544,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                 for (int h = 0; h < 2; ++h) {  // two chunk pairs; not unrolled to keep the code I-cache resident
                     tmem_ld_wait(ra);
                     tmem_ld_issue(tbase + h * 64 + 32, rb);
-                    process_chunk(ra, pos_t + h * 64, p, myLs, myLi, lane, kc, rs);
+                    process_chunk(ra, pos_t + h * 64, p, ls, li, kc, rs);
                     tmem_ld_wait(rb);
                     if (h == 0) {
                         tmem_ld_issue(tbase + 64, ra);
@@ -498,23 +554,19 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
                     }
-                    process_chunk(rb, pos_t + h * 64 + 32, p, myLs, myLi, lane, kc, rs);
+                    process_chunk(rb, pos_t + h * 64 + 32, p, ls, li, kc, rs);
                 }
             }
-            // ---- write this warp's 32 candidate lists (coalesced 128 B rows)
-            for (int r = 0; r < 32; ++r) {
-                const int64_t gr = grow0 + r;
-                if (gr >= p.n_rows) break;
-                const float es = myLs[r * 32 + lane];
-                const int ei = myLi[r * 32 + lane];
-                const int64_t o = ((int64_t)split * p.rows_pad + gr) * 32 + lane;
-                const bool keep = lane < kc;
-                p.cand_scores[o] = keep ? es : -INFINITY;
-                p.cand_ids[o] = keep ? ei : B200_PAD_ID;
-                const int cnt = __popc(__ballot_sync(B200_FULL_MASK, keep && ei != B200_PAD_ID));
-                if (lane == 0) p.cand_counts[(int64_t)split * p.rows_pad + gr] = cnt;
+            // ---- write this thread's candidate list (unsorted; select_kernel<true> orders it)
+            if (row_ok) {
+                const int64_t lrow = (int64_t)split * p.rows_pad + grow;
+                for (int e = 0; e < 32; ++e) {
+                    const bool keep = e < rs.cnt;
+                    p.cand_scores[lrow * 32 + e] = keep ? lds_f32(ls + e * 128) : -INFINITY;
+                    p.cand_ids[lrow * 32 + e] = keep ? lds_s32(li + e * 128) : B200_PAD_ID;
+                }
+                p.cand_counts[lrow] = rs.cnt;
             }
-            __syncwarp();
         }
     }
 

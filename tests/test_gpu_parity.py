@@ -183,6 +183,38 @@ def test_random_vs_oracle(rb, n_users, n_items, d, k, per_user, distance, tc_mod
             assert ranker.last_stats["n_fallback_rows"] <= max(4, n_users // 50), ranker.last_stats
 
 
+@pytest.mark.parametrize("splits", [None, "3"])
+@pytest.mark.parametrize(
+    "kernel_env",
+    [{}, {"B200_TC_STAGE": "0"}, {"B200_TC_TILE": "128"}, {"B200_TC_TILE": "128", "B200_TC_STAGE": "0"}, {"B200_TC_KERNEL": "1"}],
+    ids=["2sm256stage", "2sm256", "2sm128stage", "2sm128", "1sm"],
+)
+def test_many_work_items_per_cta(rb, monkeypatch, splits, kernel_env):
+    """More subject tiles than CTAs (persistent loop, accumulator / list / threshold hand-over between work items) and
+    forced object splits, for every tensor-core kernel variant."""
+    from rectools_b200 import _lib
+
+    for k_, v_ in kernel_env.items():
+        monkeypatch.setenv(k_, v_)
+    if splits:
+        monkeypatch.setenv("B200_TC_SPLITS", splits)
+    n_users, n_items, d, k = 60_000, 12_345, 64, 10
+    u, i = synth_factors(n_users, n_items, d, seed=77)
+    csr = synth_viewed_csr(n_users, n_items, 30)
+    ranker = rb.B200Ranker("dot", u, i)
+    sids = np.arange(n_users)
+    _, ids, scores, counts = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
+    assert ranker.last_stats["path"] == 1
+    sel = np.unique(np.concatenate([np.arange(0, n_users, 29), np.arange(n_users - 300, n_users)]))
+    _, oid, osc = rank_oracle("dot", u, i, sel, k, csr[sel], accum="f64")
+    np.testing.assert_array_equal(ids[sel].reshape(-1), oid, err_msg=str(ranker.last_stats))
+    np.testing.assert_allclose(scores[sel].reshape(-1), osc, rtol=3e-7, atol=1e-9)
+    # determinism: a second call returns bit-identical arrays
+    _, ids2, scores2, _ = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
+    np.testing.assert_array_equal(ids, ids2)
+    np.testing.assert_array_equal(scores, scores2)
+
+
 def test_edge_cases(rb):
     from rectools_b200 import _lib
 
