@@ -52,7 +52,8 @@ struct TcParams {
     int32_t* cand_ids;
     int32_t* cand_counts;     // [n_splits][rows_pad]
     int64_t rows_pad;
-    int32_t debug_mode;       // 0 = normal; 1 = no candidates (fast path only); 2 = epilogue skips the TMEM reads (measurement hooks)
+    int32_t debug_mode;       // 0 = normal; 1 = no candidates (fast path only); 2 = epilogue skips the TMEM reads; 3 = normal + cycle counters
+    long long* debug_cycles;  // mode 3: [CTA][8 epilogue warps][4] = cycles waiting for the accumulator, reading TMEM, scanning; tiles
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -218,7 +219,28 @@ struct RowState {
     int nv;       // next viewed global object id >= the stream position (B200_PAD_ID when the CSR row is exhausted)
     int64_t cur;  // index of `nv` in csr indices
     int64_t fhi;  // end of the row's CSR slice
+    uint32_t st;  // 2-SM kernel: shared-memory address of the row's shared list state (0: the list is private)
 };
+
+// Row state shared by the two threads that scan the two column halves of a row in the 2-SM kernel.
+struct SharedRow {
+    float thr;         // minimum of the full list (-inf while filling, +inf for padded rows)
+    uint32_t cnt_min;  // entries | (slot of the minimum << 8)
+    uint32_t tag;      // work item this state belongs to
+    uint32_t done;     // threads that finished the work item
+    uint32_t lock;
+    uint32_t pad[3];
+};
+static_assert(sizeof(SharedRow) == 32, "SharedRow layout");
+
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.acquire.cta.shared::cta.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ void row_unlock(uint32_t st) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(st + 16), "r"(0u) : "memory");
+}
 
 // Candidate lists live in shared memory as [slot][lane]: the thread that owns a row reads and writes only its own
 // column (bank = lane, conflict-free), so all 32 rows of a warp can take candidates at the same time.
@@ -239,6 +261,45 @@ __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.sh
 // minimum and re-scan for the new one (K' independent shared-memory loads; runs for all rows of the warp in parallel).
 // ls / li = shared addresses of slot 0 of this thread's column in the score / id arrays.
 __device__ __forceinline__ void list_insert(uint32_t ls, uint32_t li, int kc, RowState& rs, float val, int obj) {
+    if (rs.st != 0) {
+        // ---- 2-SM kernel: one list per row shared by two threads (slot stride 512 B = 128 rows), guarded by a spin lock
+        // (taken only on a hit; the critical section runs inside the loop so that diverged lanes cannot deadlock)
+        bool done = false;
+        while (!done) {
+            if (atoms_cas(rs.st + 16, 0u, 1u) == 0u) {
+                const float cur = lds_f32(rs.st);
+                if (val > cur) {
+                    const uint32_t cm = (uint32_t)lds_s32(rs.st + 4);
+                    int cnt = cm & 0xff;
+                    const int slot = cnt < kc ? cnt : (int)(cm >> 8);
+                    sts_f32(ls + slot * 512, val);
+                    sts_s32(li + slot * 512, obj);
+                    if (cnt < kc && ++cnt < kc) {
+                        sts_s32(rs.st + 4, cnt);
+                    } else {
+                        float mn = INFINITY;
+                        int mp = 0;
+#pragma unroll 8
+                        for (int e = 0; e < kc; ++e) {
+                            const float x = lds_f32(ls + e * 512);
+                            if (x < mn) {
+                                mn = x;
+                                mp = e;
+                            }
+                        }
+                        sts_f32(rs.st, mn);
+                        sts_s32(rs.st + 4, kc | (mp << 8));
+                        rs.thr = fmaxf(rs.thr, mn);
+                    }
+                } else {
+                    rs.thr = fmaxf(rs.thr, cur);  // the other thread raised the bar meanwhile
+                }
+                row_unlock(rs.st);
+                done = true;
+            }
+        }
+        return;
+    }
     const int slot = rs.cnt < kc ? rs.cnt : rs.minpos;
     sts_f32(ls + slot * 128, val);
     sts_s32(li + slot * 128, obj);
@@ -254,7 +315,7 @@ __device__ __forceinline__ void list_insert(uint32_t ls, uint32_t li, int kc, Ro
         }
     }
     rs.minpos = mp;
-    rs.thr = fmaxf(rs.thr, mn);  // never loosen a bound borrowed from the row's other list
+    rs.thr = fmaxf(rs.thr, mn);
 }
 
 // Objects are visited in ascending id order, so the filter_pairs_csr lookup is a merge, not a search: `nv` trails
@@ -505,6 +566,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;  // padded rows never produce candidates
             rs.cnt = 0;
             rs.minpos = 0;
+            rs.st = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
