@@ -247,9 +247,9 @@ TcPlan plan_tc(int d_pad) {
 TcPlan plan_tc2(int d_pad, int tile_n) {
     TcPlan pl{};
     pl.kblocks = d_pad / tc::KBLK;
-    pl.s_sub = 2;  // 256 subject rows per CTA pair
+    pl.s_sub = 2;  // two candidate lists per row (one per column half)
     const int a = pl.kblocks * tc::BLK_BYTES;
-    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * (int)sizeof(tc::SharedRow);  // two parities of lists + row state
+    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8 + tc::HITQ_CAP * 256 * 8;  // lists, thresholds, hit rings
     const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
     const int blkb = tile_n / 2 * tc::KBLK * 2;  // object block bytes per CTA
     int stages = (tc::SMEM_LIMIT - fixed) / blkb;
@@ -672,7 +672,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.n_pos = n_pos;
             tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
             const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
-            const int lists_per_split = 1;  // one candidate list per row and object split
+            const int lists_per_split = use_2sm ? 2 : 1;
             tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
             // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
             int best_splits = 1;
@@ -707,12 +707,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.cand_ids = E->cand_ids.as<int32_t>();
             tp.cand_counts = E->cand_counts.as<int32_t>();
             tp.rows_pad = rows_pad;
-            if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hooks (modes 1, 2: invalid results)
-            if (tp.debug_mode == 3) {
-                E->scratch.ensure(sizeof(long long) * 4 * 8 * 2 * (size_t)E->sm_count + 64);
-                CK(cudaMemsetAsync(E->scratch.p, 0, sizeof(long long) * 4 * 8 * 2 * (size_t)E->sm_count, st));
-                tp.debug_cycles = E->scratch.as<long long>();
-            }
+            if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
             S.n_splits = best_splits;
             const int n_work = tp.n_row_tiles * tp.n_splits;
             CK(cudaEventRecord(E->ev[2], st));
@@ -736,23 +731,6 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             CK(cudaEventRecord(E->ev[3], st));
             S.n_launches++;
 
-            if (tp.debug_mode == 3) {  // per-warp cycle counters of the epilogue (measurement hook)
-                const int n = 4 * 8 * 2 * std::min(n_work, n_units);
-                std::vector<long long> h(n);
-                CK(cudaMemcpyAsync(h.data(), tp.debug_cycles, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                double w = 0, l = 0, pr = 0, t = 0, prmax = 0;
-                for (int i = 0; i < n; i += 4) {
-                    w += h[i];
-                    l += h[i + 1];
-                    pr += h[i + 2];
-                    t += h[i + 3];
-                    if (h[i + 3] > 0) prmax = std::max(prmax, (double)h[i + 2] / h[i + 3]);
-                }
-                if (t > 0)
-                    fprintf(stderr, "[b200 tc debug] per tile and warp: wait %.0f  tmem-load %.0f  scan %.0f cycles (max warp scan %.0f), tiles/warp %.0f\n",
-                            w / t, l / t, pr / t, prmax, t / (n / 4));
-            }
             // fp64 re-score of the candidates + certificate
             E->fb_rows.ensure(sizeof(int32_t) * (n_rows + 1));
             int32_t* fb_count = E->fb_rows.as<int32_t>() + n_rows;

@@ -82,13 +82,13 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 //        that is busy inserting candidates.
 // STAGE = true: an epilogue warp first copies its whole [32 rows x TN/2 columns] slice of the accumulator to registers
 //        (one wide tcgen05.ld), hands the TMEM buffer back at once and only then scans the scores, so the MMA of tile
-//        t+2 never waits for candidate insertion of tile t (320 threads per CTA to afford ~200 registers per thread).
+//        t+2 never waits for candidate insertion of tile t (320 threads per CTA to afford 192 registers per thread).
 template <bool STAGE>
 struct Tc2Threads {
     static constexpr int EPI0 = STAGE ? 2 : EPI_WARP0;  // first epilogue warp; (warp & 3) is its TMEM lane quarter
     static constexpr int ALLOC_WARP = STAGE ? 0 : 2;    // TMEM allocation / release (warp 0 also runs the TMA role)
-    static constexpr int THREADS = (EPI0 + 8) * 32;     // 320 threads (~200 registers each) when staging
-    static constexpr int MAXREG = STAGE ? 200 : 168;
+    static constexpr int THREADS = (EPI0 + 8) * 32;     // 320 threads (192 registers each) when staging
+    static constexpr int MAXREG = STAGE ? 192 : 168;
 };
 
 template <int TN, int NBUF, bool STAGE>
@@ -104,13 +104,15 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
     const int KB = p.kblocks, NS = p.n_stages;
     uint8_t* sA = smem;                                      // [KB] blocks: this CTA's 128 subject rows
     uint8_t* sB = sA + (size_t)KB * BLK_BYTES;               // [NS] blocks: this CTA's half of the object tiles
-    // candidate lists: ONE list per subject row, shared by the two threads that scan the row's two column halves
-    // (halves the inserts and the candidates to re-score); two copies (work-item parity) so that a thread that is
-    // already on the next subject tile never touches the list its partner is still finishing
-    float* sLs = reinterpret_cast<float*>(sB + (size_t)NS * BLKB_BYTES);  // [2 parities][32 slots][128 rows] scores
-    int* sLi = reinterpret_cast<int*>(sLs + 2 * 32 * TILE_M);            // [2][32][128] object ids
-    SharedRow* sSt = reinterpret_cast<SharedRow*>(sLi + 2 * 32 * TILE_M);  // [2][128] threshold / count / lock
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sSt + 2 * TILE_M);
+    float* sLs = reinterpret_cast<float*>(sB + (size_t)NS * BLKB_BYTES);  // [2 halves][128 rows][32] candidate scores
+    int* sLi = reinterpret_cast<int*>(sLs + 2 * TILE_M * 32);            // [2][128][32] candidate ids
+    // [2][128] published (threshold, work-item tag) pairs: the tag keeps a warp that has already moved on to the next
+    // subject tile from adopting its partner's threshold of the previous one
+    unsigned long long* sThr = reinterpret_cast<unsigned long long*>(sLi + 2 * TILE_M * 32);
+    // per-thread rings of pending hits: [HITQ_CAP slots][256 epilogue threads] scores, then positions
+    float* sQv = reinterpret_cast<float*>(sThr + 2 * TILE_M);
+    int* sQp = reinterpret_cast<int*>(sQv + HITQ_CAP * 256);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sQp + HITQ_CAP * 256);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES);
@@ -139,11 +141,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
         tma_prefetch_desc(&tm_obj);
     }
     constexpr int EPI0 = Tc2Threads<STAGE>::EPI0;
-    if (warp >= EPI0) {
-        SharedRow* r0 = sSt + (warp - EPI0) * 32 + lane;
-        r0->tag = 0xFFFFFFFFu;  // a tag no work item can carry
-        r0->lock = 0u;
-    }
+    if (warp >= EPI0) sThr[(warp - EPI0) * 32 + lane] = ~0ull;  // tag no work item can carry
     if (warp == Tc2Threads<STAGE>::ALLOC_WARP) {
         tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
         tmem_relinquish_2sm();
@@ -231,42 +229,34 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
         const int ew = warp - EPI0;
         const int half = ew >> 2, quarter = warp & 3;  // column half of the tile / TMEM lane quarter (== warp % 4)
         const int wrow0 = quarter * 32;              // first CTA-local subject row of this warp
-        const int row = wrow0 + lane;  // CTA-local subject row of this thread
-        const uint32_t ls0 = smem_u32(sLs) + row * 4, li0 = smem_u32(sLi) + row * 4, st0 = smem_u32(sSt) + row * 32;
-        const int kc = p.k_cand;
-        uint32_t tile_it = 0;
+        const uint32_t ls = smem_u32(sLs + (size_t)(half * TILE_M + wrow0) * 32) + lane * 4;  // [slot][lane] arrays of this warp
+        const uint32_t li = smem_u32(sLi + (size_t)(half * TILE_M + wrow0) * 32) + lane * 4;
+        volatile unsigned long long* myThr = sThr + half * TILE_M + wrow0 + lane;
+        const volatile unsigned long long* peerThr = sThr + (half ^ 1) * TILE_M + wrow0 + lane;
         uint32_t work_tag = 0;
-        long long c_wait = 0, c_load = 0, c_proc = 0, c_tiles = 0;
-        const bool prof = p.debug_mode == 3;
+        const int kc = p.k_cand;
+        const uint32_t qv = smem_u32(sQv) + (ew * 32 + lane) * 4, qp = smem_u32(sQp) + (ew * 32 + lane) * 4;
+        uint32_t tile_it = 0;
         for (int w = pair; w < n_work; w += n_pairs, ++work_tag) {
             const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
             const int t0 = split * p.tiles_per_split;
             const int t1 = min(t0 + p.tiles_per_split, p.n_obj_tiles);
-            const int64_t grow = ((int64_t)rt * 2 + rank) * TILE_M + row;  // global subject row
+            const int64_t grow0 = ((int64_t)rt * 2 + rank) * TILE_M + wrow0;  // global row of lane 0
+            const int64_t grow = grow0 + lane;
             const bool row_ok = grow < p.n_rows;
-            const uint32_t parity = work_tag & 1;
-            const uint32_t ls = ls0 + parity * (32 * TILE_M * 4), li = li0 + parity * (32 * TILE_M * 4);
             RowState rs;
-            rs.thr = (row_ok && p.debug_mode != 1 && p.debug_mode != 2) ? -INFINITY : INFINITY;
+            rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;
             rs.cnt = 0;
             rs.minpos = 0;
-            rs.st = st0 + parity * (TILE_M * 32);
+            rs.qv = qv;
+            rs.qp = qp;
+            rs.qn = 0;
+            rs.qt = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
-            // whichever of the row's two threads gets here first resets the shared state for this work item
-            for (bool done = false; !done;) {
-                if (atoms_cas(rs.st + 16, 0u, 1u) == 0u) {
-                    if ((uint32_t)lds_s32(rs.st + 8) != work_tag) {
-                        sts_f32(rs.st, rs.thr);
-                        sts_s32(rs.st + 4, 0);
-                        sts_s32(rs.st + 12, 0);
-                        sts_s32(rs.st + 8, (int)work_tag);
-                    }
-                    row_unlock(rs.st);
-                    done = true;
-                }
-            }
+            *myThr = ((unsigned long long)work_tag << 32) | __float_as_uint(rs.thr);
+            __syncwarp();
             const int64_t pos_first = (int64_t)t0 * TILE2_N + half * HALF_N;
             if (row_ok && p.indptr && pos_first < p.n_pos) {
                 const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
@@ -285,12 +275,19 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
             }
             for (int t = t0; t < t1; ++t, ++tile_it) {
                 const uint32_t buf = tile_it % NBUF, tph = (tile_it / NBUF) & 1;
-                // pick up the row's current bar (the partner thread may have raised it; stale values are merely weaker)
-                rs.thr = fmaxf(rs.thr, lds_f32(rs.st));
-                const long long tc0 = prof ? clock64() : 0;
-                mbar_wait(bar_tfull + 8 * buf, tph);
+                // exchange thresholds with the thread that owns the other column half of this row (monotone, racy by
+                // design: a stale value is only a weaker bound)
+                *myThr = ((unsigned long long)work_tag << 32) | __float_as_uint(rs.thr);
+                {
+                    const unsigned long long pv = *peerThr;
+                    if ((uint32_t)(pv >> 32) == work_tag) rs.thr = fmaxf(rs.thr, __uint_as_float((uint32_t)pv));
+                }
+                // while the next accumulator is not ready, work off the hits this warp has queued
+                for (uint32_t spins = 0; !mbar_try_wait(bar_tfull + 8 * buf, tph); ++spins) {
+                    if (__any_sync(B200_FULL_MASK, rs.qn > 0)) hitq_drain(p, ls, li, kc, rs, 1);
+                    if (spins > (1u << 24)) __trap();  // watchdog: a protocol bug must not hang the GPU
+                }
                 tc_fence_after();
-                const long long tc1 = prof ? clock64() : 0;
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TILE2_N + half * HALF_N);
                 const int64_t pos_t = (int64_t)t * TILE2_N + half * HALF_N;
                 if (p.debug_mode == 2) {
@@ -308,19 +305,11 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * buf, 0);  // accumulator free again
-                    const long long tc2 = prof ? clock64() : 0;
                     process_chunk<0, HALF_N>(r, pos_t, p, ls, li, kc, rs);
                     process_chunk<32, HALF_N>(r, pos_t + 32, p, ls, li, kc, rs);
                     if constexpr (HALF_N == 128) {
                         process_chunk<64, HALF_N>(r, pos_t + 64, p, ls, li, kc, rs);
                         process_chunk<96, HALF_N>(r, pos_t + 96, p, ls, li, kc, rs);
-                    }
-                    if (prof) {
-                        const long long tc3 = clock64();
-                        c_wait += tc1 - tc0;
-                        c_load += tc2 - tc1;
-                        c_proc += tc3 - tc2;
-                        ++c_tiles;
                     }
                 } else {
                     uint32_t ra[32], rb[32];
@@ -342,32 +331,16 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                     }
                 }
             }
-            if (prof && lane == 0) {
-                long long* d = p.debug_cycles + ((size_t)blockIdx.x * 8 + ew) * 4;
-                d[0] = c_wait;
-                d[1] = c_load;
-                d[2] = c_proc;
-                d[3] = c_tiles;
-            }
-            // ---- the second of the row's two threads to finish writes the (unsorted) candidate list out
-            uint32_t arrived = 0;
-            for (bool done = false; !done;) {
-                if (atoms_cas(rs.st + 16, 0u, 1u) == 0u) {
-                    arrived = (uint32_t)lds_s32(rs.st + 12);
-                    sts_s32(rs.st + 12, (int)arrived + 1);
-                    row_unlock(rs.st);
-                    done = true;
-                }
-            }
-            if (arrived == 1 && row_ok) {
-                const int cnt = lds_s32(rs.st + 4) & 0xff;
-                const int64_t lrow = (int64_t)split * p.rows_pad + grow;
+            hitq_drain(p, ls, li, kc, rs, HITQ_CAP);
+            // ---- write this thread's candidate list (unsorted): list index = split * 2 + column half
+            if (row_ok) {
+                const int64_t lrow = (int64_t)(split * 2 + half) * p.rows_pad + grow;
                 for (int e = 0; e < 32; ++e) {
-                    const bool keep = e < cnt;
-                    p.cand_scores[lrow * 32 + e] = keep ? lds_f32(ls + e * 512) : -INFINITY;
-                    p.cand_ids[lrow * 32 + e] = keep ? lds_s32(li + e * 512) : B200_PAD_ID;
+                    const bool keep = e < rs.cnt;
+                    p.cand_scores[lrow * 32 + e] = keep ? lds_f32(ls + e * 128) : -INFINITY;
+                    p.cand_ids[lrow * 32 + e] = keep ? lds_s32(li + e * 128) : B200_PAD_ID;
                 }
-                p.cand_counts[lrow] = cnt;
+                p.cand_counts[lrow] = rs.cnt;
             }
         }
     }

@@ -52,8 +52,7 @@ struct TcParams {
     int32_t* cand_ids;
     int32_t* cand_counts;     // [n_splits][rows_pad]
     int64_t rows_pad;
-    int32_t debug_mode;       // 0 = normal; 1 = no candidates (fast path only); 2 = epilogue skips the TMEM reads; 3 = normal + cycle counters
-    long long* debug_cycles;  // mode 3: [CTA][8 epilogue warps][4] = cycles waiting for the accumulator, reading TMEM, scanning; tiles
+    int32_t debug_mode;       // 0 = normal; 1 = no candidates (fast path only); 2 = epilogue skips the TMEM reads (measurement hooks)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -219,28 +218,13 @@ struct RowState {
     int nv;       // next viewed global object id >= the stream position (B200_PAD_ID when the CSR row is exhausted)
     int64_t cur;  // index of `nv` in csr indices
     int64_t fhi;  // end of the row's CSR slice
-    uint32_t st;  // 2-SM kernel: shared-memory address of the row's shared list state (0: the list is private)
+    // deferred hits (2-SM kernel): ring of HITQ_CAP (score, position) pairs in shared memory, [slot][thread] layout
+    uint32_t qv, qp;  // shared addresses of this thread's slot 0 (0: no queue, hits are inserted at once)
+    int qn, qt;       // pending entries, next slot to write
 };
 
-// Row state shared by the two threads that scan the two column halves of a row in the 2-SM kernel.
-struct SharedRow {
-    float thr;         // minimum of the full list (-inf while filling, +inf for padded rows)
-    uint32_t cnt_min;  // entries | (slot of the minimum << 8)
-    uint32_t tag;      // work item this state belongs to
-    uint32_t done;     // threads that finished the work item
-    uint32_t lock;
-    uint32_t pad[3];
-};
-static_assert(sizeof(SharedRow) == 32, "SharedRow layout");
-
-__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t val) {
-    uint32_t old;
-    asm volatile("atom.acquire.cta.shared::cta.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
-    return old;
-}
-__device__ __forceinline__ void row_unlock(uint32_t st) {
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(st + 16), "r"(0u) : "memory");
-}
+constexpr int HITQ_CAP = 8;
+constexpr int HITQ_STRIDE = 256 * 4;  // bytes between slots (256 epilogue threads per CTA)
 
 // Candidate lists live in shared memory as [slot][lane]: the thread that owns a row reads and writes only its own
 // column (bank = lane, conflict-free), so all 32 rows of a warp can take candidates at the same time.
@@ -261,45 +245,6 @@ __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.sh
 // minimum and re-scan for the new one (K' independent shared-memory loads; runs for all rows of the warp in parallel).
 // ls / li = shared addresses of slot 0 of this thread's column in the score / id arrays.
 __device__ __forceinline__ void list_insert(uint32_t ls, uint32_t li, int kc, RowState& rs, float val, int obj) {
-    if (rs.st != 0) {
-        // ---- 2-SM kernel: one list per row shared by two threads (slot stride 512 B = 128 rows), guarded by a spin lock
-        // (taken only on a hit; the critical section runs inside the loop so that diverged lanes cannot deadlock)
-        bool done = false;
-        while (!done) {
-            if (atoms_cas(rs.st + 16, 0u, 1u) == 0u) {
-                const float cur = lds_f32(rs.st);
-                if (val > cur) {
-                    const uint32_t cm = (uint32_t)lds_s32(rs.st + 4);
-                    int cnt = cm & 0xff;
-                    const int slot = cnt < kc ? cnt : (int)(cm >> 8);
-                    sts_f32(ls + slot * 512, val);
-                    sts_s32(li + slot * 512, obj);
-                    if (cnt < kc && ++cnt < kc) {
-                        sts_s32(rs.st + 4, cnt);
-                    } else {
-                        float mn = INFINITY;
-                        int mp = 0;
-#pragma unroll 8
-                        for (int e = 0; e < kc; ++e) {
-                            const float x = lds_f32(ls + e * 512);
-                            if (x < mn) {
-                                mn = x;
-                                mp = e;
-                            }
-                        }
-                        sts_f32(rs.st, mn);
-                        sts_s32(rs.st + 4, kc | (mp << 8));
-                        rs.thr = fmaxf(rs.thr, mn);
-                    }
-                } else {
-                    rs.thr = fmaxf(rs.thr, cur);  // the other thread raised the bar meanwhile
-                }
-                row_unlock(rs.st);
-                done = true;
-            }
-        }
-        return;
-    }
     const int slot = rs.cnt < kc ? rs.cnt : rs.minpos;
     sts_f32(ls + slot * 128, val);
     sts_s32(li + slot * 128, obj);
@@ -315,7 +260,7 @@ __device__ __forceinline__ void list_insert(uint32_t ls, uint32_t li, int kc, Ro
         }
     }
     rs.minpos = mp;
-    rs.thr = fmaxf(rs.thr, mn);
+    rs.thr = fmaxf(rs.thr, mn);  // never loosen a bound borrowed from the row's other list
 }
 
 // Objects are visited in ascending id order, so the filter_pairs_csr lookup is a merge, not a search: `nv` trails
@@ -341,6 +286,37 @@ __device__ __forceinline__ bool csr_is_viewed(const int32_t* __restrict__ indice
         }
     }
     return rs.nv == g;
+}
+
+// Work off up to `max_n` queued hits of this thread (oldest first: the CSR cursor needs ascending objects per row).
+// A hit is re-checked against the current threshold, mapped to its object id, dropped when the object is in the
+// row's filter_pairs_csr slice, otherwise inserted into the row's candidate list.
+__device__ __forceinline__ void hitq_drain(const TcParams& p, uint32_t ls, uint32_t li, int kc, RowState& rs, int max_n) {
+    for (int n = 0; n < max_n && rs.qn > 0; ++n) {
+        const int slot = (rs.qt - rs.qn) & (HITQ_CAP - 1);
+        const float val = lds_f32(rs.qv + slot * HITQ_STRIDE);
+        const int pos = lds_s32(rs.qp + slot * HITQ_STRIDE);
+        --rs.qn;
+        if (val > rs.thr) {
+            const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : pos;
+            if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
+        }
+    }
+}
+
+// A score above the row's threshold at object position `pos`: queue it (2-SM kernel) or insert it at once.
+__device__ __forceinline__ void take_hit(const TcParams& p, uint32_t ls, uint32_t li, int kc, RowState& rs, float val, int pos) {
+    if (rs.qv != 0) {
+        if (rs.qn == HITQ_CAP) hitq_drain(p, ls, li, kc, rs, HITQ_CAP);  // ring full (dense start of a work item)
+        if (!(val > rs.thr)) return;
+        sts_f32(rs.qv + rs.qt * HITQ_STRIDE, val);
+        sts_s32(rs.qp + rs.qt * HITQ_STRIDE, pos);
+        rs.qt = (rs.qt + 1) & (HITQ_CAP - 1);
+        ++rs.qn;
+        return;
+    }
+    const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : pos;
+    if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
 }
 
 // v[j] for a run-time j without local memory: 5-level select tree (31 SEL), cheaper than spilling the chunk.
@@ -388,10 +364,7 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], float g0, float
             const float val = select32(v, j);
             if (val > rs.thr) {  // the threshold may have risen since the mask was built
                 const int64_t pos = pos0 + j;
-                if (pos < p.n_pos) {
-                    const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
-                    if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
-                }
+                if (pos < p.n_pos) take_hit(p, ls, li, kc, rs, val, (int)pos);
             }
         }
     }
@@ -566,7 +539,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;  // padded rows never produce candidates
             rs.cnt = 0;
             rs.minpos = 0;
-            rs.st = 0;
+            rs.qv = rs.qp = 0;
+            rs.qn = rs.qt = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
