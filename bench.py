@@ -442,7 +442,7 @@ def main():
             "parallelism": f"items sharded over {world} GPU(s), NCCL all-gather + merge" if world > 1 else "single GPU",
             "l2": "inputs larger than L2 (fp16 item shard %.0f MB + users %.0f MB per step)"
             % (n_loc * info["d_pad"] * 2 / 1e6, a.users * info["d_pad"] * 2 / 1e6),
-            "engine": {kk: timed_stats[0][kk] for kk in ("path", "k_cand", "n_splits", "n_fallback_rows")} if timed_stats else {},
+            "engine": {kk: timed_stats[0][kk] for kk in ("path", "k_cand", "n_splits", "n_fallback_rows", "n_exact_rows")} if timed_stats else {},
             "device": info["device_name"],
         },
         "e2e": e2e,

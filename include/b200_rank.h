@@ -110,7 +110,8 @@ typedef struct b200_rank_stats {
     int32_t k_cand;          /* candidates kept per row and item split by the tensor-core pass */
     int32_t n_splits;        /* item splits of the main kernel */
     int32_t n_launches;      /* kernels launched by this call */
-    int64_t n_fallback_rows; /* rows whose certificate failed and that were re-ranked exhaustively */
+    int64_t n_fallback_rows; /* rows whose certificate failed after the first tensor-core pass (re-ranked with wider lists) */
+    int64_t n_exact_rows;    /* rows that still failed and were ranked by the exhaustive fp64 kernel */
     float ms_main;           /* CUDA-event time of the dominant kernel (tensor-core pass or exhaustive kernel) */
     float ms_total;          /* CUDA-event time of the whole call on the engine stream (copies included) */
     float ms_h2d;            /* host->device staging inside ms_total */

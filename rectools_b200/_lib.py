@@ -57,6 +57,7 @@ class Stats(C.Structure):
         ("n_splits", C.c_int32),
         ("n_launches", C.c_int32),
         ("n_fallback_rows", C.c_int64),
+        ("n_exact_rows", C.c_int64),
         ("ms_main", C.c_float),
         ("ms_total", C.c_float),
         ("ms_h2d", C.c_float),

@@ -205,10 +205,10 @@ void prepare_objects(b200_rank_engine* E, int tc_mode) {
     const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
     const int grid = grid_for(E->n_obj_pad * 32, 256);
     if (E->tc_dtype == B200_TC_FP16)
-        convert_rows_kernel<__half, false><<<grid, 256, 0, E->st>>>(E->obj32_ptr, nullptr, n, E->n_obj_pad, d, E->d_pad, norms,
+        convert_rows_kernel<__half, false><<<grid, 256, 0, E->st>>>(E->obj32_ptr, nullptr, nullptr, n, E->n_obj_pad, d, E->d_pad, norms,
                                                                     E->obj_exp, 1, E->obj16.as<__half>(), nullptr);
     else
-        convert_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, E->st>>>(E->obj32_ptr, nullptr, n, E->n_obj_pad, d, E->d_pad,
+        convert_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, E->st>>>(E->obj32_ptr, nullptr, nullptr, n, E->n_obj_pad, d, E->d_pad,
                                                                            norms, 0, 0, E->obj16.as<__nv_bfloat16>(), nullptr);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(E->st));
@@ -249,7 +249,7 @@ TcPlan plan_tc2(int d_pad, int tile_n) {
     pl.kblocks = d_pad / tc::KBLK;
     pl.s_sub = 2;  // two candidate lists per row (one per column half)
     const int a = pl.kblocks * tc::BLK_BYTES;
-    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8 + tc::HITQ_CAP * 256 * 8;  // lists, thresholds, hit rings
+    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8;
     const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
     const int blkb = tile_n / 2 * tc::KBLK * 2;  // object block bytes per CTA
     int stages = (tc::SMEM_LIMIT - fixed) / blkb;
@@ -616,27 +616,23 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             return fail(B200_E_UNSUPPORTED, "b200_rank_topk: tensor-core path unavailable (tc_dtype=%d, k=%d, d_pad=%d, n_pos=%lld)",
                         E->tc_dtype, k_out, E->d_pad, (long long)n_pos);
 
-        if (!use_tc) {
-            S.path = 0;
-            run_exact(nullptr, n_rows, true);
-        } else {
-            S.path = 1;
-            S.tc_dtype = E->tc_dtype;
-            S.k_cand = k_cand;
+        // One tensor-core candidate pass + fp64 re-score + certificate over `n_sel` rows (rows_dev == nullptr: all rows).
+        // Rows whose certificate fails are appended to `fb_list`; returns their number.
+        auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int32_t* fb_list, int32_t* fb_count, bool timed) -> int64_t {
             const bool bf16 = E->tc_dtype == B200_TC_BF16;
             const int rows_per_cta = pl.s_sub * tc::TILE_M;
-            const int64_t rows_pad = round_up(n_rows, rows_per_cta);
+            const int64_t rows_pad = round_up(n_sel, rows_per_cta);
             // subjects -> 16-bit, per-row power-of-two scale
             E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
             E->row_exp.ensure(sizeof(int32_t) * rows_pad);
             {
                 const int grid = grid_for(rows_pad * 32, 256);
                 if (!bf16)
-                    convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(sub32, rowmap, n_rows, rows_pad, d, E->d_pad, nullptr, 0, 1,
-                                                                            E->sub16.as<__half>(), E->row_exp.as<int32_t>());
+                    convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad, nullptr,
+                                                                            0, 1, E->sub16.as<__half>(), E->row_exp.as<int32_t>());
                 else
-                    convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(sub32, rowmap, n_rows, rows_pad, d, E->d_pad, nullptr,
-                                                                                   0, 0, E->sub16.as<__nv_bfloat16>(),
+                    convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad,
+                                                                                   nullptr, 0, 0, E->sub16.as<__nv_bfloat16>(),
                                                                                    E->row_exp.as<int32_t>());
                 CK(cudaGetLastError());
                 S.n_launches++;
@@ -647,28 +643,28 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             int64_t obj_rows = E->n_obj_pad;
             if (wl) {
                 const int64_t npad = round_up(n_pos, tc::TILE_N);
-                E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
-                const int chunks = E->d_pad * 2 / 16;
-                gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), wl, n_pos, npad, chunks,
-                                                                                 E->obj16_wl.as<uint4>());
-                CK(cudaGetLastError());
-                S.n_launches++;
+                if (timed) {  // the gather is reused by a re-rank pass of the same call
+                    E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
+                    const int chunks = E->d_pad * 2 / 16;
+                    gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), wl, n_pos, npad, chunks,
+                                                                                     E->obj16_wl.as<uint4>());
+                    CK(cudaGetLastError());
+                    S.n_launches++;
+                }
                 obj_base = E->obj16_wl.p;
                 obj_rows = npad;
             }
-            CUtensorMap tm_obj;
-            if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16, obj_box_rows))
-                return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (objects)");
-            CUtensorMap tm_sub;
-            if (!make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
-                return fail(B200_E_CUDA, "b200_rank_topk: cuTensorMapEncodeTiled failed (subjects)");
+            CUtensorMap tm_obj, tm_sub;
+            if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16, obj_box_rows) ||
+                !make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
+                throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled", __LINE__};
 
             tc::TcParams tp{};
             tp.s_sub = pl.s_sub;
             tp.kblocks = pl.kblocks;
             tp.n_stages = pl.n_stages;
-            tp.k_cand = k_cand;
-            tp.n_rows = n_rows;
+            tp.k_cand = kc;
+            tp.n_rows = n_sel;
             tp.n_pos = n_pos;
             tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
             const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
@@ -698,6 +694,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.pos2obj = wl;
             tp.indptr = indptr;
             tp.indices = indices;
+            tp.row_ids = rows_dev;
             tp.id_off = (int32_t)E->id_offset;
             const int n_lists = best_splits * lists_per_split;
             E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * 32);
@@ -708,9 +705,9 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.cand_counts = E->cand_counts.as<int32_t>();
             tp.rows_pad = rows_pad;
             if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
-            S.n_splits = best_splits;
+            if (timed) S.n_splits = best_splits;
             const int n_work = tp.n_row_tiles * tp.n_splits;
-            CK(cudaEventRecord(E->ev[2], st));
+            if (timed) CK(cudaEventRecord(E->ev[2], st));
             if (use_2sm) {
                 const int grid = 2 * std::min(n_work, n_units);
                 bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
@@ -728,12 +725,10 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                 tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
             }
             CK(cudaGetLastError());
-            CK(cudaEventRecord(E->ev[3], st));
+            if (timed) CK(cudaEventRecord(E->ev[3], st));
             S.n_launches++;
 
             // fp64 re-score of the candidates + certificate
-            E->fb_rows.ensure(sizeof(int32_t) * (n_rows + 1));
-            int32_t* fb_count = E->fb_rows.as<int32_t>() + n_rows;
             CK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
             SelectParams sp{};
             sp.in_scores = tp.cand_scores;
@@ -741,8 +736,9 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             sp.in_counts = tp.cand_counts;
             sp.n_lists = n_lists;
             sp.L = 32;
-            sp.n_sel = n_rows;
+            sp.n_sel = n_sel;
             sp.list_stride_rows = rows_pad;
+            sp.rows = rows_dev;
             sp.k_out = k_out;
             sp.k0 = 0;
             sp.kp = k_out;
@@ -754,7 +750,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             sp.objects = E->obj32_ptr;
             sp.obj_norms = norms;
             sp.d = d;
-            sp.k_cand = k_cand;
+            sp.k_cand = kc;
             sp.row_exp = E->row_exp.as<int32_t>();
             sp.obj_exp = E->obj_exp;
             const double rho = bf16 ? 0.001953125 /*2^-9*/ : 0.00048828125 /*2^-11*/;
@@ -762,17 +758,44 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                                  std::sqrt((double)d) * 1.4551915e-11 /*2^-36*/);
             sp.max_obj_norm = E->max_obj_norm;
             sp.fb_count = fb_count;
-            sp.fb_rows = E->fb_rows.as<int32_t>();
+            sp.fb_rows = fb_list;
             const size_t sel_smem = (size_t)SEL_WARPS * d * sizeof(float);
-            if (sel_smem > 64 * 1024) return fail(B200_E_UNSUPPORTED, "b200_rank_topk: d too large for the re-score kernel");
-            select_kernel<true><<<grid_for(n_rows, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
+            select_kernel<true><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
             CK(cudaGetLastError());
             S.n_launches++;
             CK(cudaMemcpyAsync(E->h_pinned, fb_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            const int64_t n_fb = E->h_pinned[0];
+            return (int64_t)E->h_pinned[0];
+        };
+
+        if (!use_tc) {
+            S.path = 0;
+            run_exact(nullptr, n_rows, true);
+        } else {
+            S.path = 1;
+            S.tc_dtype = E->tc_dtype;
+            S.k_cand = k_cand;
+            if ((size_t)SEL_WARPS * d * sizeof(float) > 64 * 1024)
+                return fail(B200_E_UNSUPPORTED, "b200_rank_topk: d too large for the re-score kernel");
+            // two failure lists of n_rows entries + two counters
+            E->fb_rows.ensure(sizeof(int32_t) * (2 * n_rows + 2));
+            int32_t* fb1 = E->fb_rows.as<int32_t>();
+            int32_t* fb2 = fb1 + n_rows;
+            int32_t* cnt = fb2 + n_rows;
+            int64_t n_fb = run_tc(nullptr, n_rows, k_cand, fb1, cnt, true);
             S.n_fallback_rows = n_fb;
-            if (n_fb > 0) run_exact(E->fb_rows.as<int32_t>(), n_fb, false);
+            // second chance for rows whose certificate failed: same pass with the widest candidate lists (32), which
+            // only near-exact ties survive; whatever is left goes to the exhaustive fp64 kernel
+            if (n_fb > 0 && k_cand < 32) {
+                n_fb = run_tc(fb1, n_fb, 32, fb2, cnt + 1, false);
+                fb1 = fb2;
+            }
+            S.n_exact_rows = n_fb;
+            if (n_fb > 0) {
+                const int tc_splits = S.n_splits;
+                run_exact(fb1, n_fb, false);
+                S.n_splits = tc_splits;  // report the splits of the main kernel, not of the re-rank
+            }
         }
 
         // ---------------- results back

@@ -61,9 +61,10 @@ __host__ __device__ __forceinline__ int fp16_scale_exp(float amax) {
 // One warp per output row: out[row, 0:d_pad] = T( x[src_row, :] (/ norm) * 2^e ), zero padded in rows and columns.
 // PER_ROW_EXP: e is chosen per row (subjects) and written to row_exp; otherwise `fixed_exp` (objects) is used.
 template <typename T, bool PER_ROW_EXP>
-__global__ void convert_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_map, int64_t n,
-                                    int64_t n_pad, int d, int d_pad, const float* __restrict__ norms, int fixed_exp,
-                                    int use_scale, T* __restrict__ out, int32_t* __restrict__ row_exp) {
+__global__ void convert_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_map,
+                                    const int32_t* __restrict__ sel_rows, int64_t n, int64_t n_pad, int d, int d_pad,
+                                    const float* __restrict__ norms, int fixed_exp, int use_scale, T* __restrict__ out,
+                                    int32_t* __restrict__ row_exp) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= n_pad) return;
@@ -72,7 +73,8 @@ __global__ void convert_rows_kernel(const float* __restrict__ x, const int64_t* 
         for (int j = lane; j < d_pad; j += 32) o[j] = to_tc<T>(0.f);
         return;
     }
-    const int64_t src = row_map ? row_map[row] : row;
+    const int64_t lrow = sel_rows ? (int64_t)sel_rows[row] : row;  // compact batch row -> logical row -> physical row
+    const int64_t src = row_map ? row_map[lrow] : lrow;
     const float* xr = x + src * d;
     const float inv = norms ? norms[src] : 1.f;
     int e = fixed_exp;

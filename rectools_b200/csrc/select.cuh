@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectPara
             for (int o = 16; o > 0; o >>= 1) thr_approx = fmaxf(thr_approx, __shfl_xor_sync(B200_FULL_MASK, thr_approx, o));
             const float e_k = __shfl_sync(B200_FULL_MASK, run_s, p.kp - 1);
             // approximate scores are in units scaled by 2^(row_exp + obj_exp)
-            const int ex = (p.row_exp ? p.row_exp[lrow] : 0) + p.obj_exp;
+            const int ex = (p.row_exp ? p.row_exp[sel] : 0) + p.obj_exp;  // row_exp is indexed by batch row
             const double thr = ldexp((double)thr_approx, -ex);
             const double eps = (double)p.eps_rel * sqrt(unorm2) * (double)p.max_obj_norm;
             // one fp32 ulp of slack: a discarded object whose exact score rounds up to e_k could tie with a smaller id

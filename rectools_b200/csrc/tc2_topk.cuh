@@ -82,17 +82,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 //        that is busy inserting candidates.
 // STAGE = true: an epilogue warp first copies its whole [32 rows x TN/2 columns] slice of the accumulator to registers
 //        (one wide tcgen05.ld), hands the TMEM buffer back at once and only then scans the scores, so the MMA of tile
-//        t+2 never waits for candidate insertion of tile t (320 threads per CTA to afford 192 registers per thread).
+//        t+2 never waits for candidate insertion of tile t (352 threads per CTA to afford ~180 registers per thread).
 template <bool STAGE>
 struct Tc2Threads {
-    static constexpr int EPI0 = STAGE ? 2 : EPI_WARP0;  // first epilogue warp; (warp & 3) is its TMEM lane quarter
-    static constexpr int ALLOC_WARP = STAGE ? 0 : 2;    // TMEM allocation / release (warp 0 also runs the TMA role)
-    static constexpr int THREADS = (EPI0 + 8) * 32;     // 320 threads (192 registers each) when staging
-    static constexpr int MAXREG = STAGE ? 192 : 168;
+    static constexpr int EPI0 = STAGE ? 3 : EPI_WARP0;  // first epilogue warp; (warp & 3) is its TMEM lane quarter
+    static constexpr int THREADS = (EPI0 + 8) * 32;
 };
 
 template <int TN, int NBUF, bool STAGE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Threads<STAGE>::THREADS) __maxnreg__(Tc2Threads<STAGE>::MAXREG)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Threads<STAGE>::THREADS, 1)
 tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant__ CUtensorMap tm_obj, const TcParams p) {
     static_assert(TN * NBUF == TMEM_COLS && (TN == 256 || TN == 128), "accumulators must fill the 512 TMEM columns");
     constexpr int TILE2_N = TN;
@@ -109,10 +107,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
     // [2][128] published (threshold, work-item tag) pairs: the tag keeps a warp that has already moved on to the next
     // subject tile from adopting its partner's threshold of the previous one
     unsigned long long* sThr = reinterpret_cast<unsigned long long*>(sLi + 2 * TILE_M * 32);
-    // per-thread rings of pending hits: [HITQ_CAP slots][256 epilogue threads] scores, then positions
-    float* sQv = reinterpret_cast<float*>(sThr + 2 * TILE_M);
-    int* sQp = reinterpret_cast<int*>(sQv + HITQ_CAP * 256);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sQp + HITQ_CAP * 256);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sThr + 2 * TILE_M);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES);
@@ -142,7 +137,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
     }
     constexpr int EPI0 = Tc2Threads<STAGE>::EPI0;
     if (warp >= EPI0) sThr[(warp - EPI0) * 32 + lane] = ~0ull;  // tag no work item can carry
-    if (warp == Tc2Threads<STAGE>::ALLOC_WARP) {
+    if (warp == 2) {
         tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
         tmem_relinquish_2sm();
     }
@@ -235,7 +230,6 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
         const volatile unsigned long long* peerThr = sThr + (half ^ 1) * TILE_M + wrow0 + lane;
         uint32_t work_tag = 0;
         const int kc = p.k_cand;
-        const uint32_t qv = smem_u32(sQv) + (ew * 32 + lane) * 4, qp = smem_u32(sQp) + (ew * 32 + lane) * 4;
         uint32_t tile_it = 0;
         for (int w = pair; w < n_work; w += n_pairs, ++work_tag) {
             const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
@@ -248,10 +242,6 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;
             rs.cnt = 0;
             rs.minpos = 0;
-            rs.qv = qv;
-            rs.qp = qp;
-            rs.qn = 0;
-            rs.qt = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
@@ -260,8 +250,9 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
             const int64_t pos_first = (int64_t)t0 * TILE2_N + half * HALF_N;
             if (row_ok && p.indptr && pos_first < p.n_pos) {
                 const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
-                int64_t lo = p.indptr[grow];
-                rs.fhi = p.indptr[grow + 1];
+                const int64_t frow = p.row_ids ? (int64_t)p.row_ids[grow] : grow;
+                int64_t lo = p.indptr[frow];
+                rs.fhi = p.indptr[frow + 1];
                 int64_t hi = rs.fhi;
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
@@ -282,11 +273,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                     const unsigned long long pv = *peerThr;
                     if ((uint32_t)(pv >> 32) == work_tag) rs.thr = fmaxf(rs.thr, __uint_as_float((uint32_t)pv));
                 }
-                // while the next accumulator is not ready, work off the hits this warp has queued
-                for (uint32_t spins = 0; !mbar_try_wait(bar_tfull + 8 * buf, tph); ++spins) {
-                    if (__any_sync(B200_FULL_MASK, rs.qn > 0)) hitq_drain(p, ls, li, kc, rs, 1);
-                    if (spins > (1u << 24)) __trap();  // watchdog: a protocol bug must not hang the GPU
-                }
+                mbar_wait(bar_tfull + 8 * buf, tph);
                 tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TILE2_N + half * HALF_N);
                 const int64_t pos_t = (int64_t)t * TILE2_N + half * HALF_N;
@@ -331,7 +318,6 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                     }
                 }
             }
-            hitq_drain(p, ls, li, kc, rs, HITQ_CAP);
             // ---- write this thread's candidate list (unsorted): list index = split * 2 + column half
             if (row_ok) {
                 const int64_t lrow = (int64_t)(split * 2 + half) * p.rows_pad + grow;
@@ -347,7 +333,7 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
 
     tc_fence_before();
     cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal its barriers / read its smem
-    if (warp == Tc2Threads<STAGE>::ALLOC_WARP) {
+    if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }

@@ -47,6 +47,7 @@ struct TcParams {
     const int32_t* pos2obj;   // nullable whitelist map
     const int64_t* indptr;    // nullable CSR filter by subject row
     const int32_t* indices;
+    const int32_t* row_ids;   // nullable: batch row -> row of the CSR filter (re-ranked subsets)
     int32_t id_off;           // global id = local object id + id_off (CSR column ids are global)
     float* cand_scores;       // [n_splits][rows_pad][32]
     int32_t* cand_ids;
@@ -218,13 +219,7 @@ struct RowState {
     int nv;       // next viewed global object id >= the stream position (B200_PAD_ID when the CSR row is exhausted)
     int64_t cur;  // index of `nv` in csr indices
     int64_t fhi;  // end of the row's CSR slice
-    // deferred hits (2-SM kernel): ring of HITQ_CAP (score, position) pairs in shared memory, [slot][thread] layout
-    uint32_t qv, qp;  // shared addresses of this thread's slot 0 (0: no queue, hits are inserted at once)
-    int qn, qt;       // pending entries, next slot to write
 };
-
-constexpr int HITQ_CAP = 8;
-constexpr int HITQ_STRIDE = 256 * 4;  // bytes between slots (256 epilogue threads per CTA)
 
 // Candidate lists live in shared memory as [slot][lane]: the thread that owns a row reads and writes only its own
 // column (bank = lane, conflict-free), so all 32 rows of a warp can take candidates at the same time.
@@ -288,37 +283,6 @@ __device__ __forceinline__ bool csr_is_viewed(const int32_t* __restrict__ indice
     return rs.nv == g;
 }
 
-// Work off up to `max_n` queued hits of this thread (oldest first: the CSR cursor needs ascending objects per row).
-// A hit is re-checked against the current threshold, mapped to its object id, dropped when the object is in the
-// row's filter_pairs_csr slice, otherwise inserted into the row's candidate list.
-__device__ __forceinline__ void hitq_drain(const TcParams& p, uint32_t ls, uint32_t li, int kc, RowState& rs, int max_n) {
-    for (int n = 0; n < max_n && rs.qn > 0; ++n) {
-        const int slot = (rs.qt - rs.qn) & (HITQ_CAP - 1);
-        const float val = lds_f32(rs.qv + slot * HITQ_STRIDE);
-        const int pos = lds_s32(rs.qp + slot * HITQ_STRIDE);
-        --rs.qn;
-        if (val > rs.thr) {
-            const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : pos;
-            if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
-        }
-    }
-}
-
-// A score above the row's threshold at object position `pos`: queue it (2-SM kernel) or insert it at once.
-__device__ __forceinline__ void take_hit(const TcParams& p, uint32_t ls, uint32_t li, int kc, RowState& rs, float val, int pos) {
-    if (rs.qv != 0) {
-        if (rs.qn == HITQ_CAP) hitq_drain(p, ls, li, kc, rs, HITQ_CAP);  // ring full (dense start of a work item)
-        if (!(val > rs.thr)) return;
-        sts_f32(rs.qv + rs.qt * HITQ_STRIDE, val);
-        sts_s32(rs.qp + rs.qt * HITQ_STRIDE, pos);
-        rs.qt = (rs.qt + 1) & (HITQ_CAP - 1);
-        ++rs.qn;
-        return;
-    }
-    const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : pos;
-    if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
-}
-
 // v[j] for a run-time j without local memory: 5-level select tree (31 SEL), cheaper than spilling the chunk.
 __device__ __forceinline__ float select32(const float (&v)[32], int j) {
     float a[16], b[8], c[4], d[2];
@@ -364,7 +328,10 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], float g0, float
             const float val = select32(v, j);
             if (val > rs.thr) {  // the threshold may have risen since the mask was built
                 const int64_t pos = pos0 + j;
-                if (pos < p.n_pos) take_hit(p, ls, li, kc, rs, val, (int)pos);
+                if (pos < p.n_pos) {
+                    const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
+                    if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
+                }
             }
         }
     }
@@ -539,8 +506,6 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;  // padded rows never produce candidates
             rs.cnt = 0;
             rs.minpos = 0;
-            rs.qv = rs.qp = 0;
-            rs.qn = rs.qt = 0;
             rs.nv = B200_PAD_ID;
             rs.cur = 0;
             rs.fhi = 0;
@@ -548,8 +513,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
                 // position the CSR cursor at the first object of this split (one lower_bound per work item)
                 const int64_t pos_first = (int64_t)t0 * TILE_N;
                 const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
-                int64_t lo = p.indptr[grow];
-                rs.fhi = p.indptr[grow + 1];
+                const int64_t frow = p.row_ids ? (int64_t)p.row_ids[grow] : grow;
+                int64_t lo = p.indptr[frow];
+                rs.fhi = p.indptr[frow + 1];
                 int64_t hi = rs.fhi;
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
