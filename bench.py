@@ -250,9 +250,9 @@ def main():
 
     def exchange_and_merge():
         assert k_loc == k, "bench shards must hold at least k items"
-        dist.all_gather_into_tensor(g_ids, o_ids)
-        dist.all_gather_into_tensor(g_sc, o_sc)
-        dist.all_gather_into_tensor(g_cnt, o_cnt)
+        dist.all_gather_into_tensor(g_ids.view(world * a.users, k), o_ids)
+        dist.all_gather_into_tensor(g_sc.view(world * a.users, k), o_sc)
+        dist.all_gather_into_tensor(g_cnt.view(world * a.users), o_cnt)
         _lib.check(lib.b200_rank_merge(local_rank, torch.cuda.current_stream().cuda_stream, world, a.users, k, g_ids.data_ptr(),
                                        g_sc.data_ptr(), g_cnt.data_ptr(), m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr()))
         launches[0] += 1 + (k + 31) // 32

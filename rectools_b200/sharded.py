@@ -181,9 +181,10 @@ class ShardedB200Ranker:
         g_ids = torch.empty((self.world, n, k), dtype=ids.dtype, device=ids.device)
         g_sc = torch.empty((self.world, n, k), dtype=sc.dtype, device=sc.device)
         g_cnt = torch.empty((self.world, n), dtype=cnt.dtype, device=cnt.device)
-        self.dist.all_gather_into_tensor(g_ids, ids.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(g_sc, sc.contiguous(), group=self.group)
-        self.dist.all_gather_into_tensor(g_cnt, cnt.contiguous(), group=self.group)
+        # (concatenated-along-dim-0 views: the form every backend accepts)
+        self.dist.all_gather_into_tensor(g_ids.view(self.world * n, k), ids.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(g_sc.view(self.world * n, k), sc.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(g_cnt.view(self.world * n), cnt.contiguous(), group=self.group)
         o_ids, o_sc, o_cnt = self.local.merge(g_ids, g_sc, g_cnt, k)
         return subject_ids, o_ids, o_sc, o_cnt
 
