@@ -600,12 +600,25 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             else
                 use_2sm = false;
         }
+        // Candidates kept per list by the tensor-core pass (K' >= k; the surplus is the certificate's safety margin).
+        // 1-SM kernel: one list per row.  2-SM kernel: two lists per row (one per column half), so a small surplus per
+        // list already gives ~2k candidates; rows where (nearly) all of the top-k fall into one half fail the
+        // certificate and take the second-chance pass.  Inserts, the dominant epilogue cost, scale with K'.
         int k_cand = 0;
-        if (k_out <= 10)
-            k_cand = 16;
-        else if (k_out <= 24)
-            k_cand = 32;
-        if (E->tc_dtype == B200_TC_BF16 && k_out <= 24) k_cand = 32;
+        const bool bf16_tc = E->tc_dtype == B200_TC_BF16;
+        if (use_2sm) {
+            const int surplus = bf16_tc ? std::max(6, k_out / 2) : std::max(2, k_out / 4);
+            if (k_out <= 24) k_cand = std::min(32, k_out + surplus);
+        } else {
+            if (k_out <= 10 && !bf16_tc)
+                k_cand = 16;
+            else if (k_out <= 24)
+                k_cand = 32;
+        }
+        if (const char* env = getenv("B200_TC_KCAND")) {  // tuning hook
+            const int forced = atoi(env);
+            if (forced >= k_out && forced <= 32) k_cand = forced;
+        }
         bool use_tc = E->tc_dtype != B200_TC_OFF && pl.ok && k_cand > 0 && !(q->flags & B200_Q_FORCE_EXACT) &&
                       n_pos >= (int64_t)k_cand * 4;
         if (use_tc && !(q->flags & B200_Q_FORCE_TC)) {
