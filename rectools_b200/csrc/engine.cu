@@ -142,13 +142,13 @@ struct b200_rank_engine {
     DevBuf out_ids, out_scores, out_counts;
     DevBuf cand_scores, cand_ids, cand_counts;
     DevBuf part_scores, part_ids;
-    DevBuf fb_rows, scratch;
+    DevBuf fb_rows, scratch, excl;
     int32_t* h_pinned = nullptr;  // small pinned scratch (fallback count)
 
     size_t hbm_bytes() const {
         const DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
                                &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
-                               &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch};
+                               &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl};
         size_t t = 0;
         for (auto* b : all) t += b->cap;
         return t;
@@ -156,7 +156,7 @@ struct b200_rank_engine {
     void free_all() {
         DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
                          &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
-                         &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch};
+                         &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl};
         for (auto* b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -526,7 +526,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
 
         // exhaustive fp64 passes over `n_sel` rows (rows_dev == nullptr: all rows)
-        auto run_exact = [&](const int32_t* rows_dev, int64_t n_sel, bool timed) {
+        auto run_exact = [&](const int32_t* rows_dev, int64_t n_sel, bool timed, int k_begin, int k_end) {
             const int64_t tiles_total = (n_pos + 31) / 32;
             const int blocks_x = grid_for(n_sel, EX_ROWS);
             int n_splits = (2 * E->sm_count + blocks_x - 1) / blocks_x;
@@ -534,8 +534,8 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             n_splits = std::min(n_splits, 1024);
             E->part_scores.ensure(sizeof(float) * (size_t)n_splits * n_sel * LIST_LEN);
             E->part_ids.ensure(sizeof(int32_t) * (size_t)n_splits * n_sel * LIST_LEN);
-            for (int k0 = 0; k0 < k_out; k0 += 32) {
-                const int kp = std::min(32, k_out - k0);
+            for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+                const int kp = std::min(32, k_end - k0);
                 ExactParams p{};
                 p.subjects = sub32;
                 p.row_map = rowmap;
@@ -559,10 +559,10 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                 p.part_scores = E->part_scores.as<float>();
                 p.part_ids = E->part_ids.as<int32_t>();
                 p.part_stride_rows = n_sel;
-                if (timed && k0 == 0) CK(cudaEventRecord(E->ev[2], st));
+                if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[2], st));
                 exact_topk_kernel<<<dim3(blocks_x, n_splits), EX_THREADS, 0, st>>>(p);
                 CK(cudaGetLastError());
-                if (timed && k0 == 0) CK(cudaEventRecord(E->ev[3], st));
+                if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[3], st));
                 SelectParams sp{};
                 sp.in_scores = E->part_scores.as<float>();
                 sp.in_ids = E->part_ids.as<int32_t>();
@@ -609,10 +609,11 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         if (use_2sm) {
             const int surplus = bf16_tc ? std::max(6, k_out / 2) : std::max(2, k_out / 4);
             if (k_out <= 24) k_cand = std::min(32, k_out + surplus);
+            else if (k_out <= 128) k_cand = 25;  // multi-pass, see below
         } else {
             if (k_out <= 10 && !bf16_tc)
                 k_cand = 16;
-            else if (k_out <= 24)
+            else if (k_out <= 128)
                 k_cand = 32;
         }
         if (const char* env = getenv("B200_TC_KCAND")) {  // tuning hook
@@ -631,7 +632,8 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
 
         // One tensor-core candidate pass + fp64 re-score + certificate over `n_sel` rows (rows_dev == nullptr: all rows).
         // Rows whose certificate fails are appended to `fb_list`; returns their number.
-        auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int32_t* fb_list, int32_t* fb_count, bool timed) -> int64_t {
+        auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int k0, int kp, int32_t* fb_list, int32_t* fb_count,
+                          bool timed) -> int64_t {
             const bool bf16 = E->tc_dtype == B200_TC_BF16;
             const int rows_per_cta = pl.s_sub * tc::TILE_M;
             const int64_t rows_pad = round_up(n_sel, rows_per_cta);
@@ -708,6 +710,11 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             tp.indptr = indptr;
             tp.indices = indices;
             tp.row_ids = rows_dev;
+            if (k0 > 0) {  // objects returned by earlier passes are excluded like viewed ones
+                tp.excl = E->excl.as<int32_t>();
+                tp.excl_stride = k_out;
+                tp.excl_n = k0;
+            }
             tp.id_off = (int32_t)E->id_offset;
             const int n_lists = best_splits * lists_per_split;
             E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * 32);
@@ -753,8 +760,8 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             sp.list_stride_rows = rows_pad;
             sp.rows = rows_dev;
             sp.k_out = k_out;
-            sp.k0 = 0;
-            sp.kp = k_out;
+            sp.k0 = k0;
+            sp.kp = kp;
             sp.out_ids = o_ids;
             sp.out_scores = o_scores;
             sp.out_counts = o_counts;
@@ -783,7 +790,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
 
         if (!use_tc) {
             S.path = 0;
-            run_exact(nullptr, n_rows, true);
+            run_exact(nullptr, n_rows, true, 0, k_out);
         } else {
             S.path = 1;
             S.tc_dtype = E->tc_dtype;
@@ -795,20 +802,40 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             int32_t* fb1 = E->fb_rows.as<int32_t>();
             int32_t* fb2 = fb1 + n_rows;
             int32_t* cnt = fb2 + n_rows;
-            int64_t n_fb = run_tc(nullptr, n_rows, k_cand, fb1, cnt, true);
-            S.n_fallback_rows = n_fb;
-            // second chance for rows whose certificate failed: same pass with the widest candidate lists (32), which
-            // only near-exact ties survive; whatever is left goes to the exhaustive fp64 kernel
-            if (n_fb > 0 && k_cand < 32) {
-                n_fb = run_tc(fb1, n_fb, 32, fb2, cnt + 1, false);
-                fb1 = fb2;
+            // k <= 24: one pass.  Larger k: passes of `k_pass` results; every pass is certified (or re-ranked) on its own and
+            // the ids returned so far are excluded from the next pass exactly like viewed objects, so the concatenation of
+            // the passes is the exact top-k in order.
+            const int k_pass = k_out <= 24 ? k_out : 20;
+            const int kc_pass = k_out <= 24 ? k_cand : (use_2sm ? (bf16_tc ? 30 : 25) : 32);
+            if (k_out > 24) E->excl.ensure(sizeof(int32_t) * (size_t)n_rows * k_out);
+            int64_t total_fb = 0, total_exact = 0;
+            for (int k0 = 0; k0 < k_out; k0 += k_pass) {
+                const int kp = std::min(k_pass, k_out - k0);
+                const int kc = std::min(32, std::max(kc_pass - (k_pass - kp), kp));
+                if (k0 > 0) {
+                    build_exclusion_kernel<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(o_ids, n_rows, k_out, k0, (int32_t)E->id_offset,
+                                                                                      E->excl.as<int32_t>());
+                    CK(cudaGetLastError());
+                    S.n_launches++;
+                }
+                int32_t* f1 = fb1;
+                int64_t n_fb = run_tc(nullptr, n_rows, kc, k0, kp, f1, cnt, k0 == 0);
+                total_fb += n_fb;
+                // second chance for rows whose certificate failed: same pass with the widest candidate lists (32), which
+                // only near-exact ties survive; whatever is left goes to the exhaustive fp64 kernel
+                if (n_fb > 0 && kc < 32) {
+                    n_fb = run_tc(f1, n_fb, 32, k0, kp, fb2, cnt + 1, false);
+                    f1 = fb2;
+                }
+                total_exact += n_fb;
+                if (n_fb > 0) {
+                    const int tc_splits = S.n_splits;
+                    run_exact(f1, n_fb, false, k0, k0 + kp);
+                    S.n_splits = tc_splits;  // report the splits of the main kernel, not of the re-rank
+                }
             }
-            S.n_exact_rows = n_fb;
-            if (n_fb > 0) {
-                const int tc_splits = S.n_splits;
-                run_exact(fb1, n_fb, false);
-                S.n_splits = tc_splits;  // report the splits of the main kernel, not of the re-rank
-            }
+            S.n_fallback_rows = total_fb;
+            S.n_exact_rows = total_exact;
         }
 
         // ---------------- results back

@@ -329,6 +329,27 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const SelectPara
     }
 }
 
+// Multi-pass ranking (k > 24 on the tensor-core path): the ids a row has received so far, sorted ascending, become the
+// row's exclusion list for the next pass (one warp per row, rank counting; unfilled slots sort last as B200_PAD_ID).
+__global__ void build_exclusion_kernel(const int32_t* __restrict__ out_ids, int64_t n_rows, int32_t k_out, int32_t k0,
+                                       int32_t id_off, int32_t* __restrict__ excl) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int32_t* src = out_ids + row * k_out;
+    for (int i = lane; i < k0; i += 32) {
+        const int32_t raw = src[i];
+        const int32_t key = raw < 0 ? B200_PAD_ID : raw + id_off;  // the kernels compare GLOBAL ids
+        int rank = 0;
+        for (int j = 0; j < k0; ++j) {
+            const int32_t rj = src[j];
+            const int32_t kj = rj < 0 ? B200_PAD_ID : rj + id_off;
+            rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
+        }
+        excl[row * k_out + rank] = key;
+    }
+}
+
 // Local object ids -> global ids of an item-sharded catalogue (unfilled slots stay -1).
 __global__ void add_offset_kernel(int32_t* ids, int64_t n, int32_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -242,27 +242,13 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;
             rs.cnt = 0;
             rs.minpos = 0;
-            rs.nv = B200_PAD_ID;
-            rs.cur = 0;
-            rs.fhi = 0;
             *myThr = ((unsigned long long)work_tag << 32) | __float_as_uint(rs.thr);
             __syncwarp();
-            const int64_t pos_first = (int64_t)t0 * TILE2_N + half * HALF_N;
-            if (row_ok && p.indptr && pos_first < p.n_pos) {
-                const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
-                const int64_t frow = p.row_ids ? (int64_t)p.row_ids[grow] : grow;
-                int64_t lo = p.indptr[frow];
-                rs.fhi = p.indptr[frow + 1];
-                int64_t hi = rs.fhi;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (__ldg(p.indices + mid) < g_first)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-                rs.cur = lo;
-                rs.nv = lo < rs.fhi ? __ldg(p.indices + lo) : B200_PAD_ID;
+            {
+                const int64_t pos_first = (int64_t)t0 * TILE2_N + half * HALF_N;
+                const bool live = row_ok && pos_first < p.n_pos;
+                const int g_first = live ? (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off : 0;
+                row_cursors_init(p, rs, live ? (p.row_ids ? (int64_t)p.row_ids[grow] : grow) : -1, g_first);
             }
             for (int t = t0; t < t1; ++t, ++tile_it) {
                 const uint32_t buf = tile_it % NBUF, tph = (tile_it / NBUF) & 1;

@@ -48,6 +48,9 @@ struct TcParams {
     const int64_t* indptr;    // nullable CSR filter by subject row
     const int32_t* indices;
     const int32_t* row_ids;   // nullable: batch row -> row of the CSR filter (re-ranked subsets)
+    const int32_t* excl;      // nullable: [rows][excl_stride] ids already returned by earlier passes (k > 24), sorted ascending
+    int32_t excl_stride;
+    int32_t excl_n;           // ids per row in `excl` (rows with fewer results are padded with B200_PAD_ID)
     int32_t id_off;           // global id = local object id + id_off (CSR column ids are global)
     float* cand_scores;       // [n_splits][rows_pad][32]
     int32_t* cand_ids;
@@ -219,6 +222,9 @@ struct RowState {
     int nv;       // next viewed global object id >= the stream position (B200_PAD_ID when the CSR row is exhausted)
     int64_t cur;  // index of `nv` in csr indices
     int64_t fhi;  // end of the row's CSR slice
+    // multi-pass ranking (k > 24): objects returned by earlier passes are excluded the same way
+    const int32_t* xrow;  // this row's sorted exclusion list (nullptr: none)
+    int xcur, xnv;        // cursor / next excluded global object id
 };
 
 // Candidate lists live in shared memory as [slot][lane]: the thread that owns a row reads and writes only its own
@@ -283,6 +289,53 @@ __device__ __forceinline__ bool csr_is_viewed(const int32_t* __restrict__ indice
     return rs.nv == g;
 }
 
+// Same merge cursor over the (short, <= k entries) list of objects already returned by earlier passes of a k > 24 query.
+__device__ __forceinline__ bool is_excluded(RowState& rs, int n, int g) {
+    while (rs.xnv < g) {
+        ++rs.xcur;
+        rs.xnv = rs.xcur < n ? __ldg(rs.xrow + rs.xcur) : B200_PAD_ID;
+    }
+    return rs.xnv == g;
+}
+
+// Position the two cursors of a row at the first object (global id g_first) of a work item.
+__device__ __forceinline__ void row_cursors_init(const TcParams& p, RowState& rs, int64_t frow, int g_first) {
+    rs.nv = B200_PAD_ID;
+    rs.cur = 0;
+    rs.fhi = 0;
+    rs.xrow = nullptr;
+    rs.xcur = 0;
+    rs.xnv = B200_PAD_ID;
+    if (frow < 0) return;
+    if (p.indptr) {
+        int64_t lo = p.indptr[frow];
+        rs.fhi = p.indptr[frow + 1];
+        int64_t hi = rs.fhi;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(p.indices + mid) < g_first)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        rs.cur = lo;
+        rs.nv = lo < rs.fhi ? __ldg(p.indices + lo) : B200_PAD_ID;
+    }
+    if (p.excl) {
+        rs.xrow = p.excl + frow * p.excl_stride;
+        int lo = 0, hi = p.excl_n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(rs.xrow + mid) < g_first)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        rs.xcur = lo;
+        rs.xnv = lo < p.excl_n ? __ldg(rs.xrow + lo) : B200_PAD_ID;
+    }
+}
+
 // v[j] for a run-time j without local memory: 5-level select tree (31 SEL), cheaper than spilling the chunk.
 __device__ __forceinline__ float select32(const float (&v)[32], int j) {
     float a[16], b[8], c[4], d[2];
@@ -330,7 +383,9 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], float g0, float
                 const int64_t pos = pos0 + j;
                 if (pos < p.n_pos) {
                     const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
-                    if (!csr_is_viewed(p.indices, rs, obj + p.id_off)) list_insert(ls, li, kc, rs, val, obj);
+                    const int g = obj + p.id_off;
+                    if (!csr_is_viewed(p.indices, rs, g) && !(rs.xrow && is_excluded(rs, p.excl_n, g)))
+                        list_insert(ls, li, kc, rs, val, obj);
                 }
             }
         }
@@ -506,26 +561,11 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant
             rs.thr = (row_ok && p.debug_mode == 0) ? -INFINITY : INFINITY;  // padded rows never produce candidates
             rs.cnt = 0;
             rs.minpos = 0;
-            rs.nv = B200_PAD_ID;
-            rs.cur = 0;
-            rs.fhi = 0;
-            if (row_ok && p.indptr && (int64_t)t0 * TILE_N < p.n_pos) {
-                // position the CSR cursor at the first object of this split (one lower_bound per work item)
+            {
                 const int64_t pos_first = (int64_t)t0 * TILE_N;
-                const int g_first = (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off;
-                const int64_t frow = p.row_ids ? (int64_t)p.row_ids[grow] : grow;
-                int64_t lo = p.indptr[frow];
-                rs.fhi = p.indptr[frow + 1];
-                int64_t hi = rs.fhi;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (__ldg(p.indices + mid) < g_first)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-                rs.cur = lo;
-                rs.nv = lo < rs.fhi ? __ldg(p.indices + lo) : B200_PAD_ID;
+                const bool live = row_ok && pos_first < p.n_pos;
+                const int g_first = live ? (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off : 0;
+                row_cursors_init(p, rs, live ? (p.row_ids ? (int64_t)p.row_ids[grow] : grow) : -1, g_first);
             }
             for (int t = t0; t < t1; ++t, ++tile_it) {
                 const uint32_t buf = tile_it & 1, tph = (tile_it >> 1) & 1;

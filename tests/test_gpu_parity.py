@@ -183,6 +183,28 @@ def test_random_vs_oracle(rb, n_users, n_items, d, k, per_user, distance, tc_mod
             assert ranker.last_stats["n_fallback_rows"] <= max(4, n_users // 50), ranker.last_stats
 
 
+@pytest.mark.parametrize("distance, k, use_wl", [("dot", 100, False), ("cosine", 100, True), ("dot", 37, False)])
+def test_multi_pass_tensor_core_large_k(rb, distance, k, use_wl):
+    """k > 24 on the tensor-core path (BASELINE config 3 shape: COSINE, K = 100, ~100 viewed): passes of 20 results,
+    earlier results excluded like viewed objects; the concatenation must be the exact top-k in order."""
+    from rectools_b200 import _lib
+
+    n_users, n_items, d = 1500, 30_000, 64
+    u, i = synth_factors(n_users, n_items, d, seed=k)
+    csr = synth_viewed_csr(n_users, n_items, 100)
+    wl = np.sort(np.random.default_rng(4).choice(n_items, 9_000, replace=False)) if use_wl else None
+    ranker = rb.B200Ranker(distance, u, i)
+    sids = np.arange(n_users)
+    _, ids, scores, counts = ranker.rank_padded(sids, k, csr, wl, flags=_lib.Q_FORCE_TC)
+    assert ranker.last_stats["path"] == 1 and (counts == k).all()
+    sel = sids[::5]
+    _, oid, osc = rank_oracle(distance, u, i, sel, k, csr[sel], wl, accum="f64")
+    if distance == "cosine":
+        osc = osc * ranker.subjects_norms[np.repeat(sel, k)]
+    np.testing.assert_array_equal(ids[sel].reshape(-1), oid, err_msg=str(ranker.last_stats))
+    np.testing.assert_allclose(scores[sel].reshape(-1), osc, rtol=3e-7, atol=1e-9)
+
+
 @pytest.mark.parametrize("splits", [None, "3"])
 @pytest.mark.parametrize(
     "kernel_env",
