@@ -80,6 +80,8 @@ class B200TorchRanker(B200Ranker):
         dev = str(device)
         if dev.startswith("cuda") and ":" in dev:
             dev_index = int(dev.split(":")[1])
+        if hasattr(objects_factors, "detach") and dev.startswith("cuda") and not objects_factors.is_cuda:
+            objects_factors = objects_factors.to(device)  # `TorchRanker` scores on `device` (rank_torch.py:135)
         super().__init__(distance, subjects_factors, objects_factors, device=dev_index)
         self.batch_size = batch_size
 

@@ -48,6 +48,10 @@ def _dense_f32(x: tp.Any) -> np.ndarray:
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
+def _is_cuda_tensor(x: tp.Any) -> bool:
+    return hasattr(x, "is_cuda") and bool(getattr(x, "is_cuda")) and hasattr(x, "data_ptr")
+
+
 def _norms_f32(x: np.ndarray) -> np.ndarray:
     """`_calc_norms(avoid_zeros=True)` (rank_implicit.py:98-105), accumulated in fp64 as the engine does."""
     n = np.sqrt(np.einsum("ij,ij->i", x, x, dtype=np.float64)).astype(np.float32)
@@ -270,6 +274,11 @@ class B200Ranker:
         self.distance = _as_distance(distance)
         if sparse.issparse(subjects_factors) and self.distance != Distance.DOT:
             raise ValueError("To use `sparse.csr_matrix` distance must be `Distance.DOT`")  # rank_implicit.py:66-67
+        if engine is None and self.distance != Distance.EUCLIDEAN and _is_cuda_tensor(objects_factors):
+            # embeddings that already live on the GPU (transformer scorers keep `item_embs` on the device,
+            # rectools/models/nn/transformers/lightning.py:391, :398): hand the device pointers over, no host round trip
+            self._init_from_device_tensors(subjects_factors, objects_factors, tc_mode)
+            return
         subjects = _dense_f32(subjects_factors)
         objects = _dense_f32(objects_factors)
         if subjects.shape[1] != objects.shape[1]:
@@ -279,6 +288,32 @@ class B200Ranker:
         self.engine = engine or Engine(objects, cosine=self.distance == Distance.COSINE, device=device, tc_mode=tc_mode)
         self.engine.set_subjects(subjects)
         self.last_stats: tp.Dict[str, tp.Any] = {}
+
+    def _init_from_device_tensors(self, subjects_factors: tp.Any, objects_factors: tp.Any, tc_mode: str) -> None:
+        import torch
+
+        objects = objects_factors.detach().to(torch.float32).contiguous()
+        dev = objects.device
+        subjects = subjects_factors
+        if not hasattr(subjects, "detach"):
+            subjects = torch.from_numpy(_dense_f32(subjects))
+        subjects = subjects.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if subjects.shape[1] != objects.shape[1]:
+            raise ValueError("subject and object factors must have the same number of columns")
+        self.n_subjects, self.n_objects = int(subjects.shape[0]), int(objects.shape[0])
+        self.subjects_norms = self.subjects_dots = None
+        if self.distance == Distance.COSINE:
+            norms = torch.linalg.vector_norm(subjects.double(), dim=1).float()
+            norms[norms == 0] = 1e-10
+            self.subjects_norms = norms.cpu().numpy()
+        torch.cuda.current_stream(dev).synchronize()
+        self._device_tensors = (subjects, objects)  # the engine references this memory: keep it alive
+        self.engine = Engine(
+            None, cosine=self.distance == Distance.COSINE, device=dev.index or 0, tc_mode=tc_mode,
+            objects_device_ptr=objects.data_ptr(), shape=(self.n_objects, int(objects.shape[1])),
+        )
+        self.engine.set_subjects_device(subjects.data_ptr(), self.n_subjects)
+        self.last_stats = {}
 
     # ------------------------------------------------------------------------------------------------------------
     def rank_padded(

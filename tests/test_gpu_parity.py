@@ -285,6 +285,26 @@ def test_edge_cases(rb):
         ranker.rank([0], k=0)
 
 
+def test_torch_ranker_signature_with_device_tensors(rb):
+    """`TorchRanker`-style construction (rank_torch.py:59-67) with embeddings already on the GPU: device pointers are
+    handed to the engine, results equal the oracle (and the reference's value-based filter semantics, rank_torch.py:143)."""
+    import torch
+
+    n_users, n_items, d, k = 700, 9_000, 48, 10
+    u, i = synth_factors(n_users, n_items, d, seed=31)
+    csr = synth_viewed_csr(n_users, n_items, 25)
+    csr.data[::7] = 0.0  # explicit zeros do not filter in TorchRanker
+    for distance in ("dot", "cosine"):
+        ranker = rb.B200TorchRanker(distance, "cuda:0", torch.from_numpy(u), torch.from_numpy(i).to("cuda:0"), batch_size=128)
+        subj, ids, scores = ranker.rank(np.arange(n_users), k, csr)
+        eff = csr.copy()
+        eff.eliminate_zeros()
+        es, eid, esc = rank_oracle(distance, u, i, np.arange(n_users), k, eff, accum="f64")
+        np.testing.assert_array_equal(subj, es)
+        np.testing.assert_array_equal(ids, eid)
+        np.testing.assert_allclose(scores, esc, rtol=2e-6, atol=1e-7)
+
+
 def test_merge_matches_unsharded(rb):
     """Item-sharded ranking: per-shard top-k with global ids + b200_rank_merge == ranking the whole catalogue."""
     import torch
