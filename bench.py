@@ -367,9 +367,19 @@ def main():
         if peak is None:
             peak, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
         achieved = flops / (ms_main * 1e-3) / 1e12
+        # dram__bytes_read + write of one launch of this kernel from the committed `ncu --set full` capture, when that
+        # capture was taken on exactly this workload (profiles/r01_ncu_tc_kernel.{txt,json}); otherwise null
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_tc_kernel.json")))
+            if world == 1 and (cap["users"], cap["items"], cap["dim"]) == (a.users, a.items, a.dim):
+                traffic = cap["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         roof = {
-            "kernel": "tc_topk_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "kernel": "tc2_topk_kernel<256,2,true> (tcgen05.mma.cta_group::2 + fused top-K' selection)", "bound": "tensor",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peak_src,
             "algorithmic": f"2*U*N_g*d = 2*{a.users}*{n_loc}*{a.dim} FLOP per launch",
             "ms_per_launch": ms_main,
             "peak_burst": peaks.get("bf16_tflops"),

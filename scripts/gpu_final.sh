@@ -8,7 +8,7 @@ run f_smoke 300 python __graft_entry__.py smoke
 run f_bench 900 python bench.py --steps 5 --warmup 3
 run f_bench_ref 900 python bench.py --impl reference --steps 3 --warmup 1
 run f_ncu_list 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/r01_launches.csv python bench.py --users 303104 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --parity-users 0
-run f_ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:topk_kernel -s 2 -c 1 -f -o $OUT/r01_prof_tc python bench.py --users 75776 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --parity-users 0
+run f_ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:topk_kernel -s 2 -c 1 -f -o $OUT/r01_prof_tc python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --parity-users 0
 
 for kc in 10 11 12 14; do
   B200_TC_KCAND=$kc timeout 300 python bench.py --users 303104 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --parity-users 64 > $OUT/kc_$kc.log 2>&1

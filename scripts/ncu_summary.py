@@ -33,11 +33,23 @@ for k in hdr:
         o.write("%-88s %s\n" % (k, d[k]))
 t_ms = float(d["gpu__time_duration.sum"]) * (1e-3 if u["gpu__time_duration.sum"].startswith("us") else 1.0)
 flops = 2.0 * users * 1e6 * 128
-dram = float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])
+def to_bytes(key):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u[key]]
+    return float(d[key]) * scale
+
+
+dram = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+waves = -(-(users // 256 + (1 if users % 256 else 0)) // 74)
 o.write(
     "\nderived: algorithmic FLOP = 2*U*N*d = %.3e -> %.0f TFLOP/s under ncu (clock-control none, cold caches); "
-    "traffic = dram read + write = %.1f %s per launch vs the compulsory %.0f MB (256 MB fp16 item shard + fp16 subjects)\n"
-    % (flops, flops / (t_ms * 1e-3) / 1e12, dram, u["dram__bytes_read.sum"], 256 + users * 256 / 1e6)
+    "traffic = dram read + write = %.3f GB per launch = %.2f x (256 MB fp16 item shard) for %d waves of subject tiles "
+    "(74 CTA pairs stream the shard in lock-step: one HBM pass per wave, the other 73 reads are L2 hits); "
+    "compulsory one-pass traffic would be %.0f MB\n"
+    % (flops, flops / (t_ms * 1e-3) / 1e12, dram / 1e9, dram / 256e6, waves, 256 + users * 256 / 1e6)
 )
+import json
+
+json.dump({"users": users, "items": 1000000, "dim": 128, "dram_bytes_per_launch": dram, "kernel_ms_under_ncu": t_ms,
+           "source": out_path}, open(out_path.replace(".txt", ".json"), "w"))
 open(out_path, "w").write(o.getvalue())
 print(o.getvalue())
