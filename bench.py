@@ -281,6 +281,7 @@ def main():
             hm_ids = torch.empty((a.users, k), dtype=torch.int32).pin_memory()
             hm_sc = torch.empty((a.users, k), dtype=torch.float32).pin_memory()
     e2e_bytes = [0, 0]
+    e2e_stats = {}
 
     def step_e2e():
         if world == 1:
@@ -300,6 +301,8 @@ def main():
                 st = dict(st, d2h_bytes=a.users * k * 8)
             torch.cuda.current_stream().synchronize()
         e2e_bytes[0], e2e_bytes[1] = st["h2d_bytes"], st["d2h_bytes"]
+        e2e_stats.clear()
+        e2e_stats.update({kk: st[kk] for kk in ("ms_total", "ms_main", "ms_h2d", "ms_d2h")})
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,6 +346,7 @@ def main():
             "value": a.users * e2e_steps / (e2e_ms / 1e3), "unit": "users/s", "steps": e2e_steps,
             "h2d_bytes_per_step": int(e2e_bytes[0]), "d2h_bytes_per_step": int(e2e_bytes[1]),
             "api": "rectools_b200.Engine.topk (C ABI b200_rank_topk) with pinned host buffers",
+            "engine_ms_last_step": dict(e2e_stats),
         }
 
     if rank != 0:
@@ -453,6 +457,7 @@ def main():
             "l2": "inputs larger than L2 (fp16 item shard %.0f MB + users %.0f MB per step)"
             % (n_loc * info["d_pad"] * 2 / 1e6, a.users * info["d_pad"] * 2 / 1e6),
             "engine": {kk: timed_stats[0][kk] for kk in ("path", "k_cand", "n_splits", "n_fallback_rows", "n_exact_rows")} if timed_stats else {},
+            "engine_ms_last_step": {kk: timed_stats[-1][kk] for kk in ("ms_total", "ms_main", "ms_h2d", "ms_d2h")} if timed_stats else {},
             "device": info["device_name"],
         },
         "e2e": e2e,
