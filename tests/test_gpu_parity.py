@@ -285,6 +285,31 @@ def test_edge_cases(rb):
         ranker.rank([0], k=0)
 
 
+def test_near_ties_are_certified_or_re_ranked(rb):
+    """Adversarial for the tensor-core candidate pass: 300 objects whose scores differ by ~1e-6 relative -- far below the
+    fp16 operand resolution -- sit at the top of every row, so the approximate pass cannot order them.  The certificate
+    must notice (rows go to the wider re-rank / the exhaustive kernel) and the returned ids must still equal the oracle."""
+    from rectools_b200 import _lib
+
+    rng = np.random.default_rng(9)
+    n_users, n_items, d, k = 600, 20_000, 64, 10
+    u = (rng.standard_normal((n_users, d)) / np.sqrt(d)).astype(np.float32)
+    i = (0.2 * rng.standard_normal((n_items, d)) / np.sqrt(d)).astype(np.float32)
+    base = u.mean(axis=0) + 0.5 * rng.standard_normal(d).astype(np.float32) / np.sqrt(d)
+    hot = rng.choice(n_items, 300, replace=False)
+    i[hot] = (3.0 * base[None, :] * (1.0 + 1e-6 * rng.standard_normal((300, 1)))).astype(np.float32)
+    u = (u * 0.05 + base[None, :]).astype(np.float32)  # every subject scores the hot objects highest, within ~1e-6 of each other
+    csr = synth_viewed_csr(n_users, n_items, 20)
+    ranker = rb.B200Ranker("dot", u, i)
+    sids = np.arange(n_users)
+    _, ids, scores, counts = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
+    stats = ranker.last_stats
+    assert stats["path"] == 1 and stats["n_fallback_rows"] > 0, stats  # the approximate pass alone could not decide
+    _, oid, osc = rank_oracle("dot", u, i, sids, k, csr, accum="f64")
+    np.testing.assert_array_equal(ids.reshape(-1), oid, err_msg=str(stats))
+    np.testing.assert_allclose(scores.reshape(-1), osc, rtol=3e-7)
+
+
 def test_torch_ranker_signature_with_device_tensors(rb):
     """`TorchRanker`-style construction (rank_torch.py:59-67) with embeddings already on the GPU: device pointers are
     handed to the engine, results equal the oracle (and the reference's value-based filter semantics, rank_torch.py:143)."""
