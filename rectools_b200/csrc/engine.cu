@@ -142,13 +142,13 @@ struct b200_rank_engine {
     DevBuf out_ids, out_scores, out_counts;
     DevBuf cand_scores, cand_ids, cand_counts;
     DevBuf part_scores, part_ids;
-    DevBuf fb_rows, scratch, excl;
+    DevBuf fb_rows, scratch, excl, carousel;
     int32_t* h_pinned = nullptr;  // small pinned scratch (fallback count)
 
     size_t hbm_bytes() const {
         const DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
                                &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
-                               &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl};
+                               &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl, &carousel};
         size_t t = 0;
         for (auto* b : all) t += b->cap;
         return t;
@@ -156,7 +156,7 @@ struct b200_rank_engine {
     void free_all() {
         DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
                          &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
-                         &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl};
+                         &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl, &carousel};
         for (auto* b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -727,6 +727,22 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
             if (timed) S.n_splits = best_splits;
             const int n_work = tp.n_row_tiles * tp.n_splits;
+            bool carousel = use_2sm;  // B200_TC_CAROUSEL=0 disables it (every work item then starts at its first object tile)
+            if (const char* env = getenv("B200_TC_CAROUSEL")) carousel = carousel && atoi(env) != 0;
+            if (carousel) {
+                const int n_pairs_run = std::min(n_work, n_units);
+                const int per_pair = (n_work + n_pairs_run - 1) / n_pairs_run;
+                const size_t n_ints = (size_t)best_splits + (size_t)n_pairs_run * per_pair;
+                E->carousel.ensure(sizeof(int32_t) * n_ints);
+                std::vector<int32_t> init(best_splits);
+                for (int sidx = 0; sidx < best_splits; ++sidx) init[sidx] = sidx * tp.tiles_per_split;
+                CK(cudaMemsetAsync(E->carousel.p, 0xFF, sizeof(int32_t) * n_ints, st));
+                CK(cudaMemcpyAsync(E->carousel.p, init.data(), sizeof(int32_t) * best_splits, cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));  // `init` is a stack buffer
+                tp.front = E->carousel.as<int32_t>();
+                tp.starts = tp.front + best_splits;
+                tp.starts_stride = per_pair;
+            }
             if (timed) CK(cudaEventRecord(E->ev[2], st));
             if (use_2sm) {
                 const int grid = 2 * std::min(n_work, n_units);

@@ -76,6 +76,24 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                  : "memory");
 }
 
+// Start tile of a work item: decided once by the leader CTA's producer thread (the current front of its object split),
+// published through global memory, read by every other role of both CTAs.
+__device__ __forceinline__ int carousel_start(const TcParams& p, int pair, uint32_t work_it, int split, int t0, int t1, bool decide) {
+    if (p.front == nullptr) return t0;
+    volatile int32_t* slot = p.starts + (size_t)pair * p.starts_stride + work_it;
+    if (decide) {
+        int s = *reinterpret_cast<volatile int32_t*>(p.front + split);
+        s = min(max(s, t0), t1 - 1);
+        *slot = s;
+        __threadfence();
+        return s;
+    }
+    int s;
+    for (uint32_t spins = 0; (s = *slot) < 0; ++spins)
+        if (spins > (1u << 26)) __trap();
+    return s;
+}
+
 // TN   = objects per tile of the CTA pair (each CTA loads TN/2 of them and owns TN accumulator columns per buffer)
 // NBUF = accumulator buffers in TMEM (NBUF * TN = 512 columns): 2 x 256 minimises MMA instructions and shared-memory
 //        operand traffic (64 B/clk per CTA), 4 x 128 (96 B/clk) lets the MMA run up to three tiles ahead of a warp
@@ -164,7 +182,15 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                 if (rank == 0) mbar_arrive_expect_tx(bar_afull, (uint32_t)(2 * KB * BLK_BYTES));
                 for (int kb = 0; kb < KB; ++kb)
                     tma_load_2d_2sm(sA_u + (uint32_t)kb * BLK_BYTES, &tm_sub, bar_afull, kb * KBLK, (rt * 2 + (int)rank) * TILE_M);
-                for (int t = t0; t < t1; ++t) {
+                const int nt = t1 - t0;
+                const int ts = carousel_start(p, pair, work_it, split, t0, t1, rank == 0);
+                for (int i = 0; i < nt; ++i) {
+                    const int t = ts + i < t1 ? ts + i : ts + i - nt;
+                    // the front is the position of the reference pair (pair 0 of each split's work items)
+                    // (measured: letting every pair overwrite it does not re-align pairs that drifted apart -- 333 GB of DRAM
+                    // reads per launch at U = 1M instead of 15 GB)
+                    if (rank == 0 && p.front && (i & 15) == 0 && pair == 0)
+                        *reinterpret_cast<volatile int32_t*>(p.front + split) = t;
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, ph ^ 1);
                         if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * BLKB_BYTES);
@@ -244,13 +270,21 @@ tc2_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
             rs.minpos = 0;
             *myThr = ((unsigned long long)work_tag << 32) | __float_as_uint(rs.thr);
             __syncwarp();
-            {
-                const int64_t pos_first = (int64_t)t0 * TILE2_N + half * HALF_N;
-                const bool live = row_ok && pos_first < p.n_pos;
+            const int nt = t1 - t0;
+            int ts = 0;
+            if (lane == 0) ts = carousel_start(p, pair, work_tag, split, t0, t1, false);
+            ts = __shfl_sync(B200_FULL_MASK, ts, 0);
+            const int64_t frow = row_ok ? (p.row_ids ? (int64_t)p.row_ids[grow] : grow) : -1;
+            auto cursors_at = [&](int tile) {  // (re)position the CSR / exclusion cursors at the first object of `tile`
+                const int64_t pos_first = (int64_t)tile * TILE2_N + half * HALF_N;
+                const bool live = frow >= 0 && pos_first < p.n_pos;
                 const int g_first = live ? (p.pos2obj ? __ldg(p.pos2obj + pos_first) : (int)pos_first) + p.id_off : 0;
-                row_cursors_init(p, rs, live ? (p.row_ids ? (int64_t)p.row_ids[grow] : grow) : -1, g_first);
-            }
-            for (int t = t0; t < t1; ++t, ++tile_it) {
+                row_cursors_init(p, rs, live ? frow : -1, g_first);
+            };
+            cursors_at(ts);
+            for (int it = 0; it < nt; ++it, ++tile_it) {
+                const int t = ts + it < t1 ? ts + it : ts + it - nt;
+                if (it > 0 && t == t0) cursors_at(t0);  // wrapped around: objects ascend again from the split's first tile
                 const uint32_t buf = tile_it % NBUF, tph = (tile_it / NBUF) & 1;
                 // exchange thresholds with the thread that owns the other column half of this row (monotone, racy by
                 // design: a stale value is only a weaker bound)

@@ -57,6 +57,11 @@ struct TcParams {
     int32_t* cand_counts;     // [n_splits][rows_pad]
     int64_t rows_pad;
     int32_t debug_mode;       // 0 = normal; 1 = no candidates (fast path only); 2 = epilogue skips the TMEM reads (measurement hooks)
+    // carousel (2-SM kernel): a work item starts streaming the objects where the other CTA pairs currently are, so that
+    // all pairs keep reading the same few MB of the object matrix and the L2 serves 73 of 74 reads (nullptr: start at t0)
+    int32_t* front;           // [n_splits] object tile most recently issued by some pair
+    int32_t* starts;          // [n_pairs][starts_stride] start tile chosen for each work item (-1: not decided yet)
+    int32_t starts_stride;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers

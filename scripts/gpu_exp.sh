@@ -1,20 +1,14 @@
 #!/bin/bash
-# Kernel-variant comparison at the full-catalogue shape (N = 1M) and at the 8-way item-sharded shape (N = 125K).
+# DRAM traffic of the fused kernel vs number of waves / carousel variant.
 OUT=gpurun_out; mkdir -p $OUT; : > $OUT/exp_summary.txt
-brief() { python - "$1" <<'PY'
-import json,sys
-try:
-    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    r=d['roofline']; p=d.get('parity') or {}
-    print('value=%.0f ms_step=%.2f ms_main=%.2f tflops=%.0f fb=%s splits=%s mism=%s'%(d['value'],d['ms_per_step'],r['ms_per_launch'],r['achieved'],d['config']['engine'].get('n_fallback_rows'),d['config']['engine'].get('n_splits'),p.get('id_mismatches')))
-except Exception as e:
-    print('ERR',e, open(sys.argv[1]).read()[-300:])
-PY
+cap() { # label, users, env...
+  local label=$1; local users=$2; shift 2
+  env "$@" timeout 900 ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum --clock-control none -k regex:topk_kernel -s 2 -c 1 --csv --log-file $OUT/tr.csv python bench.py --users $users --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --parity-users 0 > $OUT/exp_ncu.log 2>&1
+  echo "$label users=$users: $(grep -E 'dram__bytes_read|gpu__time|lts__' $OUT/tr.csv | awk -F'","' '{printf "%s=%s ", $(NF-2), $NF}' | tr -d '"')" >> $OUT/exp_summary.txt
 }
-for items in 1000000 125000; do
- for cfg in "B200_TC_KERNEL=1" "B200_TC_TILE=256" "B200_TC_TILE=256 B200_TC_STAGE=0" "B200_TC_TILE=128"; do
-  env $cfg timeout 300 python bench.py --users 303104 --items $items --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --parity-users 64 > $OUT/exp.log 2>&1
-  echo "items=$items [$cfg]: $(brief $OUT/exp.log)" >> $OUT/exp_summary.txt
- done
-done
+cap refpair 151552
+cap refpair 303104
+cap refpair 1000000
+cap lastwriter 1000000 B200_TC_DEBUG=4
+cap off 303104 B200_TC_CAROUSEL=0
 cat $OUT/exp_summary.txt
