@@ -6,7 +6,8 @@ import os
 import typing as tp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200rank.so")
+# B200_RANK_LIB: measurement hook -- load a variant build (python -m rectools_b200.build --variant NAME -DX=..) instead
+LIB_PATH = os.environ.get("B200_RANK_LIB") or os.path.join(HERE, "libb200rank.so")
 
 # mirrors of the #defines in include/b200_rank.h
 ABI_VERSION = 1

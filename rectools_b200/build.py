@@ -8,12 +8,13 @@ import os
 import shutil
 import subprocess
 import sys
+import typing as tp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rank.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "prep.cuh", "select.cuh", "tc_topk.cuh", os.path.join("..", "..", "include", "b200_rank.h")]
+HEADERS = ["common.cuh", "prep.cuh", "select.cuh", "tc_topk.cuh", "tc2_topk.cuh", os.path.join("..", "..", "include", "b200_rank.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,10 +39,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.normpath(d)) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tp.Sequence[str] = ()) -> str:
+    """`variant` / `defines`: measurement builds (libb200rank_<variant>.so with extra -D flags, loaded through the
+    B200_RANK_LIB environment variable); the product library is the plain build."""
+    out = LIB if not variant else os.path.join(HERE, f"libb200rank_{variant}.so")
+    if not variant and not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -56,8 +60,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libb200rank.so")
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=_variant,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

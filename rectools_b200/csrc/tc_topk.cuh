@@ -269,30 +269,8 @@ __device__ __forceinline__ void list_insert(uint32_t ls, uint32_t li, int kc, Ro
     rs.thr = fmaxf(rs.thr, mn);  // never loosen a bound borrowed from the row's other list
 }
 
-// Objects are visited in ascending id order, so the filter_pairs_csr lookup is a merge, not a search: `nv` trails
-// the stream and is advanced only when a candidate reaches it (two linear steps, then lower_bound on the rest).
-__device__ __forceinline__ bool csr_is_viewed(const int32_t* __restrict__ indices, RowState& rs, int g) {
-    if (rs.nv < g) {
-#pragma unroll 1
-        for (int step = 0; step < 2 && rs.nv < g; ++step) {
-            ++rs.cur;
-            rs.nv = rs.cur < rs.fhi ? __ldg(indices + rs.cur) : B200_PAD_ID;
-        }
-        if (rs.nv < g) {
-            int64_t lo = rs.cur + 1, hi = rs.fhi;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (__ldg(indices + mid) < g)
-                    lo = mid + 1;
-                else
-                    hi = mid;
-            }
-            rs.cur = lo;
-            rs.nv = lo < rs.fhi ? __ldg(indices + lo) : B200_PAD_ID;
-        }
-    }
-    return rs.nv == g;
-}
+// Objects are visited in ascending id order, so the filter_pairs_csr lookup is a merge, not a search: `nv` trails the
+// stream and is advanced only when a candidate passes it (csr_advance_coop below).
 
 // Same merge cursor over the (short, <= k entries) list of objects already returned by earlier passes of a k > 24 query.
 __device__ __forceinline__ bool is_excluded(RowState& rs, int n, int g) {
@@ -368,8 +346,49 @@ __device__ __forceinline__ unsigned hit_mask(const float (&v)[32], float thr) {
     return m;
 }
 
+// Warp-cooperative advance of ONE row's CSR cursor (the row owned by lane `src`) to the first viewed id >= that lane's
+// candidate id: all 32 lanes read 32 consecutive column ids of the row's slice at once, so a hit costs one global
+// round trip instead of a chain of dependent loads (measured bottleneck of the per-lane search: in the sparse tail of the
+// stream a chunk's slow path is entered for a single lane, whose 2 linear steps + lower_bound were ~9 dependent L2
+// reads = several tile times).  Long slices are first narrowed by a 32-ary search.
+__device__ __forceinline__ void csr_advance_coop(const int32_t* __restrict__ indices, RowState& rs, int g, int src, int lane) {
+    const int gs = __shfl_sync(B200_FULL_MASK, g, src);
+    long long base = __shfl_sync(B200_FULL_MASK, (long long)rs.cur, src) + 1;  // entries up to `cur` are < gs
+    const long long fhi = __shfl_sync(B200_FULL_MASK, (long long)rs.fhi, src);
+    int x, adv;
+    bool narrowed = false;
+    for (;;) {
+        const long long i = base + lane;
+        x = i < fhi ? __ldg(indices + i) : B200_PAD_ID;
+        adv = __popc(__ballot_sync(B200_FULL_MASK, x < gs));  // sorted slice: the lanes below gs form a prefix
+        base += adv;
+        if (adv < 32) break;
+        if (!narrowed && fhi - base > 64) {
+            // 32-ary narrowing: afterwards every entry before `base` is < gs and the answer lies within 32 entries
+            long long hi = fhi;
+            while (hi - base > 32) {
+                const long long step = (hi - base + 31) >> 5;
+                const long long pi = base + (long long)lane * step;
+                const bool below = pi < hi && __ldg(indices + pi) < gs;
+                const int c = __popc(__ballot_sync(B200_FULL_MASK, below));
+                if (c == 0) break;  // indices[base] >= gs
+                const long long nb = base + (long long)(c - 1) * step + 1;
+                if (c < 32 && base + (long long)c * step < hi) hi = base + (long long)c * step;
+                base = nb;
+            }
+            narrowed = true;
+        }
+    }
+    const int nvn = __shfl_sync(B200_FULL_MASK, x, adv);  // lane `adv` holds the first id >= gs (PAD_ID past the end)
+    if (lane == src) {
+        rs.cur = base;
+        rs.nv = nvn;
+    }
+}
+
 __device__ __forceinline__ void scan_chunk(const float (&v)[32], float g0, float g1, float g2, float g3, int64_t pos0,
                                            const TcParams& p, uint32_t ls, uint32_t li, int kc, RowState& rs) {
+    const int lane = threadIdx.x & 31;
     // per-lane bit mask of the columns above the row threshold, built only for the column groups whose maximum
     // (already known from the fast path) shows a hit somewhere in the warp
     unsigned hits = 0;
@@ -378,22 +397,30 @@ __device__ __forceinline__ void scan_chunk(const float (&v)[32], float g0, float
     if (__any_sync(B200_FULL_MASK, g2 > rs.thr)) hits |= hit_mask<18, 27>(v, rs.thr);
     if (__any_sync(B200_FULL_MASK, g3 > rs.thr)) hits |= hit_mask<27, 32>(v, rs.thr);
     // drain: every thread works through its own columns in ascending object order (what the CSR cursor needs);
-    // rows are independent, so all lanes insert concurrently
+    // rows are independent, so all lanes insert concurrently; only the (rare) cursor advances are done lane by lane
+    // with the whole warp helping
     while (__any_sync(B200_FULL_MASK, hits != 0)) {
+        bool cand = false;
+        float val = 0.f;
+        int obj = 0, g = 0;
         if (hits) {
             const int j = __ffs(hits) - 1;
             hits &= hits - 1;
-            const float val = select32(v, j);
-            if (val > rs.thr) {  // the threshold may have risen since the mask was built
-                const int64_t pos = pos0 + j;
-                if (pos < p.n_pos) {
-                    const int obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
-                    const int g = obj + p.id_off;
-                    if (!csr_is_viewed(p.indices, rs, g) && !(rs.xrow && is_excluded(rs, p.excl_n, g)))
-                        list_insert(ls, li, kc, rs, val, obj);
-                }
+            val = select32(v, j);
+            const int64_t pos = pos0 + j;
+            if (val > rs.thr && pos < p.n_pos) {  // the threshold may have risen since the mask was built
+                obj = p.pos2obj ? __ldg(p.pos2obj + pos) : (int)pos;
+                g = obj + p.id_off;
+                cand = true;
             }
         }
+        unsigned need = __ballot_sync(B200_FULL_MASK, cand && rs.nv < g);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            csr_advance_coop(p.indices, rs, g, src, lane);
+        }
+        if (cand && rs.nv != g && !(rs.xrow && is_excluded(rs, p.excl_n, g))) list_insert(ls, li, kc, rs, val, obj);
     }
 }
 
