@@ -23,6 +23,7 @@
 #include "select.cuh"
 #include "tc_topk.cuh"
 #include "tc2_topk.cuh"
+#include "tc3_topk.cuh"
 
 namespace {
 
@@ -260,6 +261,22 @@ TcPlan plan_tc2(int d_pad, int tile_n) {
     return pl;
 }
 
+// Shared-memory plan of the default kernel (tc3_topk.cuh): as plan_tc2(d_pad, 256) plus the deferred-hit FIFOs.
+TcPlan plan_tc3(int d_pad) {
+    TcPlan pl{};
+    pl.kblocks = d_pad / tc::KBLK;
+    pl.s_sub = 2;
+    const int a = pl.kblocks * tc::BLK_BYTES;
+    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8 + tc::T3_QBYTES;
+    const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
+    int stages = (tc::SMEM_LIMIT - fixed) / tc::BLK_BYTES;
+    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+    pl.ok = stages >= 2;
+    pl.n_stages = stages;
+    pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
+    return pl;
+}
+
 uint32_t make_idesc2(bool bf16, int tile_n) {
     uint32_t d = 0;
     d |= 1u << 4;
@@ -343,7 +360,8 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
             } else {
                 CK(cudaFuncSetAttribute(tc::tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
             }
-            TcPlan pl2 = plan_tc2(E->d_pad, 256), pl2b = plan_tc2(E->d_pad, 128);
+            TcPlan pl2 = plan_tc2(E->d_pad, 256), pl2b = plan_tc2(E->d_pad, 128), pl3 = plan_tc3(E->d_pad);
+            if (pl3.ok) CK(cudaFuncSetAttribute(tc::tc3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl3.smem_bytes));
             if (pl2.ok) {
                 CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
                 CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
@@ -588,12 +606,25 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         // ---------------- path choice
         TcPlan pl = plan_tc(E->d_pad);
         // 2-SM kernel (CTA pairs, cta_group::2) unless disabled or impossible; B200_TC_KERNEL=1 selects the 1-SM kernel
+        // B200_TC_KERNEL: 1 = 1-SM kernel (tc_topk.cuh), 2 = previous 2-SM kernel (tc2_topk.cuh), default 3 = tc3_topk.cuh
         bool use_2sm = (E->sm_count % 2 == 0);
-        if (const char* env = getenv("B200_TC_KERNEL")) use_2sm = use_2sm && atoi(env) != 1;
+        int kernel_gen = 3;
+        if (const char* env = getenv("B200_TC_KERNEL")) {
+            kernel_gen = atoi(env);
+            use_2sm = use_2sm && kernel_gen != 1;
+        }
         // tile width of the 2-SM kernel: 256 objects x 2 TMEM buffers (default) or 128 x 4 (B200_TC_TILE=128)
         int tile2_n = 256;
         if (const char* env = getenv("B200_TC_TILE")) tile2_n = atoi(env) == 128 ? 128 : 256;
-        if (use_2sm) {
+        bool use_gen3 = use_2sm && kernel_gen != 2 && tile2_n == 256;
+        if (use_gen3) {
+            TcPlan pl3 = plan_tc3(E->d_pad);
+            if (pl3.ok)
+                pl = pl3;
+            else
+                use_gen3 = false;
+        }
+        if (use_2sm && !use_gen3) {
             TcPlan pl2 = plan_tc2(E->d_pad, tile2_n);
             if (pl2.ok)
                 pl = pl2;
@@ -748,7 +779,9 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                 const int grid = 2 * std::min(n_work, n_units);
                 bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
                 if (const char* env = getenv("B200_TC_STAGE")) stage_regs = atoi(env) != 0;
-                if (tile2_n == 256 && stage_regs)
+                if (use_gen3)
+                    tc::tc3_topk_kernel<<<grid, tc::T3_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                else if (tile2_n == 256 && stage_regs)
                     tc::tc2_topk_kernel<256, 2, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
                 else if (tile2_n == 256)
                     tc::tc2_topk_kernel<256, 2, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);

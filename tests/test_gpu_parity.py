@@ -208,8 +208,15 @@ def test_multi_pass_tensor_core_large_k(rb, distance, k, use_wl):
 @pytest.mark.parametrize("splits", [None, "3"])
 @pytest.mark.parametrize(
     "kernel_env",
-    [{}, {"B200_TC_STAGE": "0"}, {"B200_TC_TILE": "128"}, {"B200_TC_TILE": "128", "B200_TC_STAGE": "0"}, {"B200_TC_KERNEL": "1"}],
-    ids=["2sm256stage", "2sm256", "2sm128stage", "2sm128", "1sm"],
+    [
+        {},
+        {"B200_TC_KERNEL": "2"},
+        {"B200_TC_KERNEL": "2", "B200_TC_STAGE": "0"},
+        {"B200_TC_KERNEL": "2", "B200_TC_TILE": "128"},
+        {"B200_TC_KERNEL": "2", "B200_TC_TILE": "128", "B200_TC_STAGE": "0"},
+        {"B200_TC_KERNEL": "1"},
+    ],
+    ids=["gen3", "2sm256stage", "2sm256", "2sm128stage", "2sm128", "1sm"],
 )
 def test_many_work_items_per_cta(rb, monkeypatch, splits, kernel_env):
     """More subject tiles than CTAs (persistent loop, accumulator / list / threshold hand-over between work items) and
