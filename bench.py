@@ -381,7 +381,7 @@ def main():
         except (OSError, ValueError, KeyError):
             pass
         roof = {
-            "kernel": "tc2_topk_kernel<256,2,true> (tcgen05.mma.cta_group::2 + fused top-K' selection)", "bound": "tensor",
+            "kernel": "tc3_topk_kernel (TMA -> tcgen05.mma.cta_group::2 256x256x16 -> TMEM -> fused streaming top-K' selection)", "bound": "tensor",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "peak_source": peak_src,
             "algorithmic": f"2*U*N_g*d = 2*{a.users}*{n_loc}*{a.dim} FLOP per launch",

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define B200_RANK_ABI_VERSION 1
+#define B200_RANK_ABI_VERSION 2
 
 /* error codes */
 #define B200_OK 0
@@ -112,12 +112,14 @@ typedef struct b200_rank_stats {
     int32_t n_launches;      /* kernels launched by this call */
     int64_t n_fallback_rows; /* rows whose certificate failed after the first tensor-core pass (re-ranked with wider lists) */
     int64_t n_exact_rows;    /* rows that still failed and were ranked by the exhaustive fp64 kernel */
-    float ms_main;           /* CUDA-event time of the dominant kernel (tensor-core pass or exhaustive kernel) */
+    float ms_main;           /* CUDA-event time of the dominant kernel (tensor-core pass or exhaustive kernel), summed over chunks */
     float ms_total;          /* CUDA-event time of the whole call on the engine stream (copies included) */
-    float ms_h2d;            /* host->device staging inside ms_total */
-    float ms_d2h;
+    float ms_h2d;            /* exposed host->device staging inside ms_total (first chunk; later chunks overlap with compute) */
+    float ms_d2h;            /* exposed device->host copy (last chunk) */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    int32_t n_chunks;        /* row chunks of the copy / compute pipeline (1: call not chunked) */
+    int32_t reserved;
 } b200_rank_stats;
 
 typedef struct b200_rank_info {

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_RANK_LIB") or os.path.join(HERE, "libb200rank.so")
 
 # mirrors of the #defines in include/b200_rank.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 DIST_DOT, DIST_COSINE = 0, 1
 TC_AUTO, TC_FP16, TC_BF16, TC_OFF = 0, 1, 2, 3
@@ -65,6 +65,8 @@ class Stats(C.Structure):
         ("ms_d2h", C.c_float),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
+        ("n_chunks", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
     def as_dict(self) -> tp.Dict[str, tp.Any]:

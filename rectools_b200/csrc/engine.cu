@@ -119,7 +119,9 @@ struct b200_rank_engine {
     int d = 0, d_pad = 0;
     int64_t n_obj_pad = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t cs = nullptr;          // copy stream of the chunk pipeline
     cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t evp[3] = {nullptr};     // chunk pipeline: inputs of chunk c / c+1 staged, stream hand-over
 
     // resident object data
     DevBuf obj32;     // [n_obj, d] fp32 master copy
@@ -163,8 +165,11 @@ struct b200_rank_engine {
         h_pinned = nullptr;
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : evp)
+            if (e) cudaEventDestroy(e);
         if (st) cudaStreamDestroy(st);
-        st = nullptr;
+        if (cs) cudaStreamDestroy(cs);
+        st = cs = nullptr;
     }
 };
 
@@ -340,7 +345,9 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
         E->d = d;
         E->d_pad = (int)round_up(d, tc::KBLK);
         CK(cudaStreamCreateWithFlags(&E->st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&E->cs, cudaStreamNonBlocking));
         for (auto& e : E->ev) CK(cudaEventCreate(&e));
+        for (auto& e : E->evp) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaMallocHost(&E->h_pinned, 64));
         if (flags & B200_F_OBJECTS_ON_DEVICE) {
             E->obj32_ptr = objects;
@@ -482,22 +489,38 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         CK(cudaEventRecord(E->ev[0], st));
 
         // ---------------- stage inputs
+        // Host inputs of a large call are staged in row chunks on a second stream: the copy of chunk c+1 (subject rows / ids,
+        // its slice of the CSR filter) and the copy-back of chunk c-1 run while chunk c is being ranked.  Buffers are
+        // full-size and addressed by absolute row / nnz offsets, so the kernels see the same layout with or without chunking.
         const float* sub32 = nullptr;
         const int64_t* rowmap = nullptr;
-        auto stage = [&](DevBuf& buf, const void* src, size_t bytes) -> const void* {
+        auto stage = [&](DevBuf& buf, const void* src, size_t bytes) -> const void* {  // un-chunked items, main stream
             if (in_dev) return src;
             buf.ensure(std::max<size_t>(bytes, 16));
             if (bytes) CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
             S.h2d_bytes += (int64_t)bytes;
             return buf.p;
         };
+        const bool chunk_subjects = q->subjects && !q->subject_ids && !in_dev;  // subject rows arrive in batch order
         if (q->subjects) {
             const int64_t rows_in = q->subject_ids ? q->n_subjects_total : n_rows;
-            sub32 = (const float*)stage(E->sub32, q->subjects, sizeof(float) * rows_in * d);
+            if (chunk_subjects) {
+                E->sub32.ensure(std::max<size_t>(sizeof(float) * rows_in * d, 16));
+                sub32 = E->sub32.as<float>();
+            } else {
+                sub32 = (const float*)stage(E->sub32, q->subjects, sizeof(float) * rows_in * d);
+            }
         } else {
             sub32 = E->sub32_res_ptr;
         }
-        if (q->subject_ids) rowmap = (const int64_t*)stage(E->rowmap, q->subject_ids, sizeof(int64_t) * n_rows);
+        if (q->subject_ids) {
+            if (in_dev) {
+                rowmap = q->subject_ids;
+            } else {
+                E->rowmap.ensure(std::max<size_t>(sizeof(int64_t) * n_rows, 16));
+                rowmap = E->rowmap.as<int64_t>();
+            }
+        }
         const int64_t* indptr = nullptr;
         const int32_t* indices = nullptr;
         if (q->csr_indptr) {
@@ -511,13 +534,37 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             }
             if (nnz < 0) return fail(B200_E_INVALID, "b200_rank_topk: csr_indptr[n_rows] < 0");
             if (nnz > 0 && !q->csr_indices) return fail(B200_E_INVALID, "b200_rank_topk: csr_indices is NULL");
-            indptr = (const int64_t*)stage(E->indptr, q->csr_indptr, sizeof(int64_t) * (n_rows + 1));
-            indices = (const int32_t*)stage(E->indices, q->csr_indices, sizeof(int32_t) * nnz);
+            if (in_dev) {
+                indptr = q->csr_indptr;
+                indices = q->csr_indices;
+            } else {
+                E->indptr.ensure(sizeof(int64_t) * (n_rows + 1));
+                E->indices.ensure(std::max<size_t>(sizeof(int32_t) * nnz, 16));
+                indptr = E->indptr.as<int64_t>();
+                indices = E->indices.as<int32_t>();
+            }
             if (nnz == 0) indptr = nullptr;  // an all-empty filter is no filter (cf. rank_implicit.py:169-173)
         }
         const int32_t* wl = nullptr;
         if (q->whitelist) wl = (const int32_t*)stage(E->wl, q->whitelist, sizeof(int32_t) * n_pos);
-        CK(cudaEventRecord(E->ev[1], st));
+        // host -> device copy of the chunked inputs of rows [r0, r1) on stream `s`
+        auto stage_rows = [&](int64_t r0, int64_t r1, cudaStream_t s) {
+            if (in_dev) return;
+            size_t bytes = 0;
+            auto h2d = [&](void* dst, const void* src, size_t n) {
+                if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s));
+                bytes += n;
+            };
+            if (chunk_subjects) h2d(E->sub32.as<float>() + r0 * d, q->subjects + r0 * d, sizeof(float) * (r1 - r0) * d);
+            if (q->subject_ids) h2d(E->rowmap.as<int64_t>() + r0, q->subject_ids + r0, sizeof(int64_t) * (r1 - r0));
+            if (indptr) {
+                h2d(E->indptr.as<int64_t>() + r0, q->csr_indptr + r0, sizeof(int64_t) * (r1 - r0 + 1));
+                const int64_t z0 = q->csr_indptr[r0], z1 = q->csr_indptr[r1];
+                if (z1 < z0) throw CudaError{cudaErrorInvalidValue, "csr_indptr must be non-decreasing", __LINE__};
+                h2d(E->indices.as<int32_t>() + z0, q->csr_indices + z0, sizeof(int32_t) * (z1 - z0));
+            }
+            S.h2d_bytes += (int64_t)bytes;
+        };
 
         // ---------------- outputs
         int32_t* o_ids;
@@ -535,74 +582,6 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             o_scores = E->out_scores.as<float>();
             o_counts = E->out_counts.as<int32_t>();
         }
-        init_outputs_kernel<<<grid_for(std::max<int64_t>(n_rows * k_out, n_rows), 256), 256, 0, st>>>(o_ids, o_scores, o_counts,
-                                                                                                   n_rows, k_out);
-        CK(cudaGetLastError());
-        S.n_launches++;
-
-        const bool cosine = E->distance == B200_DIST_COSINE;
-        const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
-
-        // exhaustive fp64 passes over `n_sel` rows (rows_dev == nullptr: all rows)
-        auto run_exact = [&](const int32_t* rows_dev, int64_t n_sel, bool timed, int k_begin, int k_end) {
-            const int64_t tiles_total = (n_pos + 31) / 32;
-            const int blocks_x = grid_for(n_sel, EX_ROWS);
-            int n_splits = (2 * E->sm_count + blocks_x - 1) / blocks_x;
-            n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_splits, tiles_total / 64));
-            n_splits = std::min(n_splits, 1024);
-            E->part_scores.ensure(sizeof(float) * (size_t)n_splits * n_sel * LIST_LEN);
-            E->part_ids.ensure(sizeof(int32_t) * (size_t)n_splits * n_sel * LIST_LEN);
-            for (int k0 = k_begin; k0 < k_end; k0 += 32) {
-                const int kp = std::min(32, k_end - k0);
-                ExactParams p{};
-                p.subjects = sub32;
-                p.row_map = rowmap;
-                p.rows = rows_dev;
-                p.n_sel_dev = nullptr;
-                p.n_sel = n_sel;
-                p.objects = E->obj32_ptr;
-                p.pos2obj = wl;
-                p.n_pos = n_pos;
-                p.d = d;
-                p.obj_norms = norms;
-                p.indptr = indptr;
-                p.indices = indices;
-                p.id_off = (int32_t)E->id_offset;
-                p.k_out = k_out;
-                p.k0 = k0;
-                p.kp = kp;
-                p.out_ids = o_ids;
-                p.out_scores = o_scores;
-                p.out_counts = o_counts;
-                p.part_scores = E->part_scores.as<float>();
-                p.part_ids = E->part_ids.as<int32_t>();
-                p.part_stride_rows = n_sel;
-                if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[2], st));
-                exact_topk_kernel<<<dim3(blocks_x, n_splits), EX_THREADS, 0, st>>>(p);
-                CK(cudaGetLastError());
-                if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[3], st));
-                SelectParams sp{};
-                sp.in_scores = E->part_scores.as<float>();
-                sp.in_ids = E->part_ids.as<int32_t>();
-                sp.in_counts = nullptr;
-                sp.n_lists = n_splits;
-                sp.L = LIST_LEN;
-                sp.n_sel = n_sel;
-                sp.list_stride_rows = n_sel;
-                sp.rows = rows_dev;
-                sp.k_out = k_out;
-                sp.k0 = k0;
-                sp.kp = kp;
-                sp.out_ids = o_ids;
-                sp.out_scores = o_scores;
-                sp.out_counts = o_counts;
-                select_kernel<false><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
-                CK(cudaGetLastError());
-                S.n_launches += 2;
-            }
-            S.n_splits = n_splits;
-        };
-
         // ---------------- path choice
         TcPlan pl = plan_tc(E->d_pad);
         // 2-SM kernel (CTA pairs, cta_group::2) unless disabled or impossible; B200_TC_KERNEL=1 selects the 1-SM kernel
@@ -657,248 +636,369 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             // tiny problems are cheaper (and exercised) on the exhaustive kernel
             if ((double)n_rows * (double)n_pos < 4.0e6) use_tc = false;
         }
+        if (use_tc && (size_t)SEL_WARPS * d * sizeof(float) > 64 * 1024)
+            return fail(B200_E_UNSUPPORTED, "b200_rank_topk: d too large for the re-score kernel");
         if ((q->flags & B200_Q_FORCE_TC) && !use_tc)
             return fail(B200_E_UNSUPPORTED, "b200_rank_topk: tensor-core path unavailable (tc_dtype=%d, k=%d, d_pad=%d, n_pos=%lld)",
                         E->tc_dtype, k_out, E->d_pad, (long long)n_pos);
 
-        // One tensor-core candidate pass + fp64 re-score + certificate over `n_sel` rows (rows_dev == nullptr: all rows).
-        // Rows whose certificate fails are appended to `fb_list`; returns their number.
-        auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int k0, int kp, int32_t* fb_list, int32_t* fb_count,
-                          bool timed) -> int64_t {
-            const bool bf16 = E->tc_dtype == B200_TC_BF16;
-            const int rows_per_cta = pl.s_sub * tc::TILE_M;
-            const int64_t rows_pad = round_up(n_sel, rows_per_cta);
-            // subjects -> 16-bit, per-row power-of-two scale
-            E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
-            E->row_exp.ensure(sizeof(int32_t) * rows_pad);
-            {
-                const int grid = grid_for(rows_pad * 32, 256);
-                if (!bf16)
-                    convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad, nullptr,
-                                                                            0, 1, E->sub16.as<__half>(), E->row_exp.as<int32_t>());
-                else
-                    convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad,
-                                                                                   nullptr, 0, 0, E->sub16.as<__nv_bfloat16>(),
-                                                                                   E->row_exp.as<int32_t>());
+        // ---------------- rank the rows of one chunk (the parameters shadow the whole-call values of the same names)
+        bool wl_gathered = false;  // the whitelist gather of the 16-bit objects is shared by all chunks / passes of a call
+        auto compute_rows = [&](int64_t n_rows, const float* sub32, const int64_t* rowmap, const int64_t* indptr, int32_t* o_ids,
+                                float* o_scores, int32_t* o_counts) {
+            init_outputs_kernel<<<grid_for(std::max<int64_t>(n_rows * k_out, n_rows), 256), 256, 0, st>>>(o_ids, o_scores, o_counts,
+                                                                                                       n_rows, k_out);
+            CK(cudaGetLastError());
+            S.n_launches++;
+
+            const bool cosine = E->distance == B200_DIST_COSINE;
+            const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
+
+            // exhaustive fp64 passes over `n_sel` rows (rows_dev == nullptr: all rows)
+            auto run_exact = [&](const int32_t* rows_dev, int64_t n_sel, bool timed, int k_begin, int k_end) {
+                const int64_t tiles_total = (n_pos + 31) / 32;
+                const int blocks_x = grid_for(n_sel, EX_ROWS);
+                int n_splits = (2 * E->sm_count + blocks_x - 1) / blocks_x;
+                n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_splits, tiles_total / 64));
+                n_splits = std::min(n_splits, 1024);
+                E->part_scores.ensure(sizeof(float) * (size_t)n_splits * n_sel * LIST_LEN);
+                E->part_ids.ensure(sizeof(int32_t) * (size_t)n_splits * n_sel * LIST_LEN);
+                for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+                    const int kp = std::min(32, k_end - k0);
+                    ExactParams p{};
+                    p.subjects = sub32;
+                    p.row_map = rowmap;
+                    p.rows = rows_dev;
+                    p.n_sel_dev = nullptr;
+                    p.n_sel = n_sel;
+                    p.objects = E->obj32_ptr;
+                    p.pos2obj = wl;
+                    p.n_pos = n_pos;
+                    p.d = d;
+                    p.obj_norms = norms;
+                    p.indptr = indptr;
+                    p.indices = indices;
+                    p.id_off = (int32_t)E->id_offset;
+                    p.k_out = k_out;
+                    p.k0 = k0;
+                    p.kp = kp;
+                    p.out_ids = o_ids;
+                    p.out_scores = o_scores;
+                    p.out_counts = o_counts;
+                    p.part_scores = E->part_scores.as<float>();
+                    p.part_ids = E->part_ids.as<int32_t>();
+                    p.part_stride_rows = n_sel;
+                    if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[2], st));
+                    exact_topk_kernel<<<dim3(blocks_x, n_splits), EX_THREADS, 0, st>>>(p);
+                    CK(cudaGetLastError());
+                    if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[3], st));
+                    SelectParams sp{};
+                    sp.in_scores = E->part_scores.as<float>();
+                    sp.in_ids = E->part_ids.as<int32_t>();
+                    sp.in_counts = nullptr;
+                    sp.n_lists = n_splits;
+                    sp.L = LIST_LEN;
+                    sp.n_sel = n_sel;
+                    sp.list_stride_rows = n_sel;
+                    sp.rows = rows_dev;
+                    sp.k_out = k_out;
+                    sp.k0 = k0;
+                    sp.kp = kp;
+                    sp.out_ids = o_ids;
+                    sp.out_scores = o_scores;
+                    sp.out_counts = o_counts;
+                    select_kernel<false><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
+                    CK(cudaGetLastError());
+                    S.n_launches += 2;
+                }
+                S.n_splits = n_splits;
+            };
+
+            // One tensor-core candidate pass + fp64 re-score + certificate over `n_sel` rows (rows_dev == nullptr: all rows).
+            // Rows whose certificate fails are appended to `fb_list`; returns their number.
+            auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int k0, int kp, int32_t* fb_list, int32_t* fb_count,
+                              bool timed) -> int64_t {
+                const bool bf16 = E->tc_dtype == B200_TC_BF16;
+                const int rows_per_cta = pl.s_sub * tc::TILE_M;
+                const int64_t rows_pad = round_up(n_sel, rows_per_cta);
+                // subjects -> 16-bit, per-row power-of-two scale
+                E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
+                E->row_exp.ensure(sizeof(int32_t) * rows_pad);
+                {
+                    const int grid = grid_for(rows_pad * 32, 256);
+                    if (!bf16)
+                        convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad, nullptr,
+                                                                                0, 1, E->sub16.as<__half>(), E->row_exp.as<int32_t>());
+                    else
+                        convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad,
+                                                                                       nullptr, 0, 0, E->sub16.as<__nv_bfloat16>(),
+                                                                                       E->row_exp.as<int32_t>());
+                    CK(cudaGetLastError());
+                    S.n_launches++;
+                }
+                // objects: resident 16-bit copy, or a whitelist gather of it
+                const int obj_box_rows = use_2sm ? tile2_n / 2 : 128;  // object rows one CTA loads per ring block
+                const void* obj_base = E->obj16.p;
+                int64_t obj_rows = E->n_obj_pad;
+                if (wl) {
+                    const int64_t npad = round_up(n_pos, tc::TILE_N);
+                    if (!wl_gathered) {  // shared by every chunk / pass / re-rank of the call
+                        wl_gathered = true;
+                        E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
+                        const int chunks = E->d_pad * 2 / 16;
+                        gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), wl, n_pos, npad, chunks,
+                                                                                         E->obj16_wl.as<uint4>());
+                        CK(cudaGetLastError());
+                        S.n_launches++;
+                    }
+                    obj_base = E->obj16_wl.p;
+                    obj_rows = npad;
+                }
+                CUtensorMap tm_obj, tm_sub;
+                if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16, obj_box_rows) ||
+                    !make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
+                    throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled", __LINE__};
+
+                tc::TcParams tp{};
+                tp.s_sub = pl.s_sub;
+                tp.kblocks = pl.kblocks;
+                tp.n_stages = pl.n_stages;
+                tp.k_cand = kc;
+                tp.n_rows = n_sel;
+                tp.n_pos = n_pos;
+                tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
+                const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
+                const int lists_per_split = use_2sm ? 2 : 1;
+                tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
+                // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
+                int best_splits = 1;
+                double best_eff = -1.0;
+                const int max_splits = std::max(1, std::min(16, tp.n_obj_tiles * (tile_n / 128) / 32));
+                const int n_units = use_2sm ? E->sm_count / 2 : E->sm_count;  // CTAs or CTA pairs working concurrently
+                for (int s = 1; s <= max_splits; ++s) {
+                    const double work = (double)tp.n_row_tiles * s;
+                    const double waves = std::ceil(work / n_units);
+                    const double eff = work / (waves * n_units) - 0.01 * (s - 1);
+                    if (eff > best_eff + 1e-9) {
+                        best_eff = eff;
+                        best_splits = s;
+                    }
+                }
+                if (const char* env = getenv("B200_TC_SPLITS")) {  // tuning / test hook
+                    const int forced = atoi(env);
+                    if (forced >= 1 && forced <= max_splits) best_splits = forced;
+                }
+                tp.n_splits = best_splits;
+                tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
+                tp.idesc = use_2sm ? make_idesc2(bf16, tile2_n) : make_idesc(bf16);
+                tp.pos2obj = wl;
+                tp.indptr = indptr;
+                tp.indices = indices;
+                tp.row_ids = rows_dev;
+                if (k0 > 0) {  // objects returned by earlier passes are excluded like viewed ones
+                    tp.excl = E->excl.as<int32_t>();
+                    tp.excl_stride = k_out;
+                    tp.excl_n = k0;
+                }
+                tp.id_off = (int32_t)E->id_offset;
+                const int n_lists = best_splits * lists_per_split;
+                E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * 32);
+                E->cand_ids.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad * 32);
+                E->cand_counts.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad);
+                tp.cand_scores = E->cand_scores.as<float>();
+                tp.cand_ids = E->cand_ids.as<int32_t>();
+                tp.cand_counts = E->cand_counts.as<int32_t>();
+                tp.rows_pad = rows_pad;
+                if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
+                if (timed) S.n_splits = best_splits;
+                const int n_work = tp.n_row_tiles * tp.n_splits;
+                bool carousel = use_2sm;  // B200_TC_CAROUSEL=0 disables it (every work item then starts at its first object tile)
+                if (const char* env = getenv("B200_TC_CAROUSEL")) carousel = carousel && atoi(env) != 0;
+                if (carousel) {
+                    const int n_pairs_run = std::min(n_work, n_units);
+                    const int per_pair = (n_work + n_pairs_run - 1) / n_pairs_run;
+                    const size_t n_ints = (size_t)best_splits + (size_t)n_pairs_run * per_pair;
+                    E->carousel.ensure(sizeof(int32_t) * n_ints);
+                    std::vector<int32_t> init(best_splits);
+                    for (int sidx = 0; sidx < best_splits; ++sidx) init[sidx] = sidx * tp.tiles_per_split;
+                    CK(cudaMemsetAsync(E->carousel.p, 0xFF, sizeof(int32_t) * n_ints, st));
+                    CK(cudaMemcpyAsync(E->carousel.p, init.data(), sizeof(int32_t) * best_splits, cudaMemcpyHostToDevice, st));
+                    CK(cudaStreamSynchronize(st));  // `init` is a stack buffer
+                    tp.front = E->carousel.as<int32_t>();
+                    tp.starts = tp.front + best_splits;
+                    tp.starts_stride = per_pair;
+                }
+                if (timed) CK(cudaEventRecord(E->ev[2], st));
+                if (use_2sm) {
+                    const int grid = 2 * std::min(n_work, n_units);
+                    bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
+                    if (const char* env = getenv("B200_TC_STAGE")) stage_regs = atoi(env) != 0;
+                    if (use_gen3)
+                        tc::tc3_topk_kernel<<<grid, tc::T3_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                    else if (tile2_n == 256 && stage_regs)
+                        tc::tc2_topk_kernel<256, 2, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                    else if (tile2_n == 256)
+                        tc::tc2_topk_kernel<256, 2, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                    else if (stage_regs)
+                        tc::tc2_topk_kernel<128, 4, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                    else
+                        tc::tc2_topk_kernel<128, 4, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                } else {
+                    const int grid = std::min(n_work, n_units);
+                    tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                }
+                CK(cudaGetLastError());
+                if (timed) CK(cudaEventRecord(E->ev[3], st));
+                S.n_launches++;
+
+                // fp64 re-score of the candidates + certificate
+                CK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
+                SelectParams sp{};
+                sp.in_scores = tp.cand_scores;
+                sp.in_ids = tp.cand_ids;
+                sp.in_counts = tp.cand_counts;
+                sp.n_lists = n_lists;
+                sp.L = 32;
+                sp.n_sel = n_sel;
+                sp.list_stride_rows = rows_pad;
+                sp.rows = rows_dev;
+                sp.k_out = k_out;
+                sp.k0 = k0;
+                sp.kp = kp;
+                sp.out_ids = o_ids;
+                sp.out_scores = o_scores;
+                sp.out_counts = o_counts;
+                sp.subjects = sub32;
+                sp.row_map = rowmap;
+                sp.objects = E->obj32_ptr;
+                sp.obj_norms = norms;
+                sp.d = d;
+                sp.k_cand = kc;
+                sp.row_exp = E->row_exp.as<int32_t>();
+                sp.obj_exp = E->obj_exp;
+                const double rho = bf16 ? 0.001953125 /*2^-9*/ : 0.00048828125 /*2^-11*/;
+                sp.eps_rel = (float)(2.0 * rho + rho * rho + (double)E->d_pad * 4.76837158e-7 /*2^-21*/ +
+                                     std::sqrt((double)d) * 1.4551915e-11 /*2^-36*/);
+                sp.max_obj_norm = E->max_obj_norm;
+                sp.fb_count = fb_count;
+                sp.fb_rows = fb_list;
+                const size_t sel_smem = (size_t)SEL_WARPS * d * sizeof(float);
+                select_kernel<true><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
+                CK(cudaGetLastError());
+                S.n_launches++;
+                CK(cudaMemcpyAsync(E->h_pinned, fb_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (timed) {
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, E->ev[2], E->ev[3]));
+                    S.ms_main += ms;
+                }
+                return (int64_t)E->h_pinned[0];
+            };
+
+            if (!use_tc) {
+                S.path = 0;
+                run_exact(nullptr, n_rows, true, 0, k_out);
+            } else {
+                S.path = 1;
+                S.tc_dtype = E->tc_dtype;
+                S.k_cand = k_cand;
+                // two failure lists of n_rows entries + two counters
+                E->fb_rows.ensure(sizeof(int32_t) * (2 * n_rows + 2));
+                int32_t* fb1 = E->fb_rows.as<int32_t>();
+                int32_t* fb2 = fb1 + n_rows;
+                int32_t* cnt = fb2 + n_rows;
+                // k <= 24: one pass.  Larger k: passes of `k_pass` results; every pass is certified (or re-ranked) on its own and
+                // the ids returned so far are excluded from the next pass exactly like viewed objects, so the concatenation of
+                // the passes is the exact top-k in order.
+                const int k_pass = k_out <= 24 ? k_out : 20;
+                const int kc_pass = k_out <= 24 ? k_cand : (use_2sm ? (bf16_tc ? 30 : 25) : 32);
+                if (k_out > 24) E->excl.ensure(sizeof(int32_t) * (size_t)n_rows * k_out);
+                int64_t total_fb = 0, total_exact = 0;
+                for (int k0 = 0; k0 < k_out; k0 += k_pass) {
+                    const int kp = std::min(k_pass, k_out - k0);
+                    const int kc = std::min(32, std::max(kc_pass - (k_pass - kp), kp));
+                    if (k0 > 0) {
+                        build_exclusion_kernel<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(o_ids, n_rows, k_out, k0, (int32_t)E->id_offset,
+                                                                                          E->excl.as<int32_t>());
+                        CK(cudaGetLastError());
+                        S.n_launches++;
+                    }
+                    int32_t* f1 = fb1;
+                    int64_t n_fb = run_tc(nullptr, n_rows, kc, k0, kp, f1, cnt, k0 == 0);
+                    total_fb += n_fb;
+                    // second chance for rows whose certificate failed: same pass with the widest candidate lists (32), which
+                    // only near-exact ties survive; whatever is left goes to the exhaustive fp64 kernel
+                    if (n_fb > 0 && kc < 32) {
+                        n_fb = run_tc(f1, n_fb, 32, k0, kp, fb2, cnt + 1, false);
+                        f1 = fb2;
+                    }
+                    total_exact += n_fb;
+                    if (n_fb > 0) {
+                        const int tc_splits = S.n_splits;
+                        run_exact(f1, n_fb, false, k0, k0 + kp);
+                        S.n_splits = tc_splits;  // report the splits of the main kernel, not of the re-rank
+                    }
+                }
+                S.n_fallback_rows += total_fb;
+                S.n_exact_rows += total_exact;
+            }
+
+            if (E->id_offset != 0) {
+                add_offset_kernel<<<grid_for(n_rows * k_out, 256), 256, 0, st>>>(o_ids, n_rows * k_out, (int32_t)E->id_offset);
                 CK(cudaGetLastError());
                 S.n_launches++;
             }
-            // objects: resident 16-bit copy, or a whitelist gather of it
-            const int obj_box_rows = use_2sm ? tile2_n / 2 : 128;  // object rows one CTA loads per ring block
-            const void* obj_base = E->obj16.p;
-            int64_t obj_rows = E->n_obj_pad;
-            if (wl) {
-                const int64_t npad = round_up(n_pos, tc::TILE_N);
-                if (timed) {  // the gather is reused by a re-rank pass of the same call
-                    E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
-                    const int chunks = E->d_pad * 2 / 16;
-                    gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), wl, n_pos, npad, chunks,
-                                                                                     E->obj16_wl.as<uint4>());
-                    CK(cudaGetLastError());
-                    S.n_launches++;
-                }
-                obj_base = E->obj16_wl.p;
-                obj_rows = npad;
+            if (!use_tc) {  // (the tensor-core path reads its kernel time after the synchronisation of every pass)
+                CK(cudaStreamSynchronize(st));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, E->ev[2], E->ev[3]));
+                S.ms_main += ms;
             }
-            CUtensorMap tm_obj, tm_sub;
-            if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16, obj_box_rows) ||
-                !make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
-                throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled", __LINE__};
-
-            tc::TcParams tp{};
-            tp.s_sub = pl.s_sub;
-            tp.kblocks = pl.kblocks;
-            tp.n_stages = pl.n_stages;
-            tp.k_cand = kc;
-            tp.n_rows = n_sel;
-            tp.n_pos = n_pos;
-            tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
-            const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
-            const int lists_per_split = use_2sm ? 2 : 1;
-            tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
-            // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
-            int best_splits = 1;
-            double best_eff = -1.0;
-            const int max_splits = std::max(1, std::min(16, tp.n_obj_tiles * (tile_n / 128) / 32));
-            const int n_units = use_2sm ? E->sm_count / 2 : E->sm_count;  // CTAs or CTA pairs working concurrently
-            for (int s = 1; s <= max_splits; ++s) {
-                const double work = (double)tp.n_row_tiles * s;
-                const double waves = std::ceil(work / n_units);
-                const double eff = work / (waves * n_units) - 0.01 * (s - 1);
-                if (eff > best_eff + 1e-9) {
-                    best_eff = eff;
-                    best_splits = s;
-                }
-            }
-            if (const char* env = getenv("B200_TC_SPLITS")) {  // tuning / test hook
-                const int forced = atoi(env);
-                if (forced >= 1 && forced <= max_splits) best_splits = forced;
-            }
-            tp.n_splits = best_splits;
-            tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
-            tp.idesc = use_2sm ? make_idesc2(bf16, tile2_n) : make_idesc(bf16);
-            tp.pos2obj = wl;
-            tp.indptr = indptr;
-            tp.indices = indices;
-            tp.row_ids = rows_dev;
-            if (k0 > 0) {  // objects returned by earlier passes are excluded like viewed ones
-                tp.excl = E->excl.as<int32_t>();
-                tp.excl_stride = k_out;
-                tp.excl_n = k0;
-            }
-            tp.id_off = (int32_t)E->id_offset;
-            const int n_lists = best_splits * lists_per_split;
-            E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * 32);
-            E->cand_ids.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad * 32);
-            E->cand_counts.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad);
-            tp.cand_scores = E->cand_scores.as<float>();
-            tp.cand_ids = E->cand_ids.as<int32_t>();
-            tp.cand_counts = E->cand_counts.as<int32_t>();
-            tp.rows_pad = rows_pad;
-            if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
-            if (timed) S.n_splits = best_splits;
-            const int n_work = tp.n_row_tiles * tp.n_splits;
-            bool carousel = use_2sm;  // B200_TC_CAROUSEL=0 disables it (every work item then starts at its first object tile)
-            if (const char* env = getenv("B200_TC_CAROUSEL")) carousel = carousel && atoi(env) != 0;
-            if (carousel) {
-                const int n_pairs_run = std::min(n_work, n_units);
-                const int per_pair = (n_work + n_pairs_run - 1) / n_pairs_run;
-                const size_t n_ints = (size_t)best_splits + (size_t)n_pairs_run * per_pair;
-                E->carousel.ensure(sizeof(int32_t) * n_ints);
-                std::vector<int32_t> init(best_splits);
-                for (int sidx = 0; sidx < best_splits; ++sidx) init[sidx] = sidx * tp.tiles_per_split;
-                CK(cudaMemsetAsync(E->carousel.p, 0xFF, sizeof(int32_t) * n_ints, st));
-                CK(cudaMemcpyAsync(E->carousel.p, init.data(), sizeof(int32_t) * best_splits, cudaMemcpyHostToDevice, st));
-                CK(cudaStreamSynchronize(st));  // `init` is a stack buffer
-                tp.front = E->carousel.as<int32_t>();
-                tp.starts = tp.front + best_splits;
-                tp.starts_stride = per_pair;
-            }
-            if (timed) CK(cudaEventRecord(E->ev[2], st));
-            if (use_2sm) {
-                const int grid = 2 * std::min(n_work, n_units);
-                bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
-                if (const char* env = getenv("B200_TC_STAGE")) stage_regs = atoi(env) != 0;
-                if (use_gen3)
-                    tc::tc3_topk_kernel<<<grid, tc::T3_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                else if (tile2_n == 256 && stage_regs)
-                    tc::tc2_topk_kernel<256, 2, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                else if (tile2_n == 256)
-                    tc::tc2_topk_kernel<256, 2, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                else if (stage_regs)
-                    tc::tc2_topk_kernel<128, 4, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                else
-                    tc::tc2_topk_kernel<128, 4, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-            } else {
-                const int grid = std::min(n_work, n_units);
-                tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-            }
-            CK(cudaGetLastError());
-            if (timed) CK(cudaEventRecord(E->ev[3], st));
-            S.n_launches++;
-
-            // fp64 re-score of the candidates + certificate
-            CK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
-            SelectParams sp{};
-            sp.in_scores = tp.cand_scores;
-            sp.in_ids = tp.cand_ids;
-            sp.in_counts = tp.cand_counts;
-            sp.n_lists = n_lists;
-            sp.L = 32;
-            sp.n_sel = n_sel;
-            sp.list_stride_rows = rows_pad;
-            sp.rows = rows_dev;
-            sp.k_out = k_out;
-            sp.k0 = k0;
-            sp.kp = kp;
-            sp.out_ids = o_ids;
-            sp.out_scores = o_scores;
-            sp.out_counts = o_counts;
-            sp.subjects = sub32;
-            sp.row_map = rowmap;
-            sp.objects = E->obj32_ptr;
-            sp.obj_norms = norms;
-            sp.d = d;
-            sp.k_cand = kc;
-            sp.row_exp = E->row_exp.as<int32_t>();
-            sp.obj_exp = E->obj_exp;
-            const double rho = bf16 ? 0.001953125 /*2^-9*/ : 0.00048828125 /*2^-11*/;
-            sp.eps_rel = (float)(2.0 * rho + rho * rho + (double)E->d_pad * 4.76837158e-7 /*2^-21*/ +
-                                 std::sqrt((double)d) * 1.4551915e-11 /*2^-36*/);
-            sp.max_obj_norm = E->max_obj_norm;
-            sp.fb_count = fb_count;
-            sp.fb_rows = fb_list;
-            const size_t sel_smem = (size_t)SEL_WARPS * d * sizeof(float);
-            select_kernel<true><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
-            CK(cudaGetLastError());
-            S.n_launches++;
-            CK(cudaMemcpyAsync(E->h_pinned, fb_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            return (int64_t)E->h_pinned[0];
         };
 
-        if (!use_tc) {
-            S.path = 0;
-            run_exact(nullptr, n_rows, true, 0, k_out);
-        } else {
-            S.path = 1;
-            S.tc_dtype = E->tc_dtype;
-            S.k_cand = k_cand;
-            if ((size_t)SEL_WARPS * d * sizeof(float) > 64 * 1024)
-                return fail(B200_E_UNSUPPORTED, "b200_rank_topk: d too large for the re-score kernel");
-            // two failure lists of n_rows entries + two counters
-            E->fb_rows.ensure(sizeof(int32_t) * (2 * n_rows + 2));
-            int32_t* fb1 = E->fb_rows.as<int32_t>();
-            int32_t* fb2 = fb1 + n_rows;
-            int32_t* cnt = fb2 + n_rows;
-            // k <= 24: one pass.  Larger k: passes of `k_pass` results; every pass is certified (or re-ranked) on its own and
-            // the ids returned so far are excluded from the next pass exactly like viewed objects, so the concatenation of
-            // the passes is the exact top-k in order.
-            const int k_pass = k_out <= 24 ? k_out : 20;
-            const int kc_pass = k_out <= 24 ? k_cand : (use_2sm ? (bf16_tc ? 30 : 25) : 32);
-            if (k_out > 24) E->excl.ensure(sizeof(int32_t) * (size_t)n_rows * k_out);
-            int64_t total_fb = 0, total_exact = 0;
-            for (int k0 = 0; k0 < k_out; k0 += k_pass) {
-                const int kp = std::min(k_pass, k_out - k0);
-                const int kc = std::min(32, std::max(kc_pass - (k_pass - kp), kp));
-                if (k0 > 0) {
-                    build_exclusion_kernel<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(o_ids, n_rows, k_out, k0, (int32_t)E->id_offset,
-                                                                                      E->excl.as<int32_t>());
-                    CK(cudaGetLastError());
-                    S.n_launches++;
-                }
-                int32_t* f1 = fb1;
-                int64_t n_fb = run_tc(nullptr, n_rows, kc, k0, kp, f1, cnt, k0 == 0);
-                total_fb += n_fb;
-                // second chance for rows whose certificate failed: same pass with the widest candidate lists (32), which
-                // only near-exact ties survive; whatever is left goes to the exhaustive fp64 kernel
-                if (n_fb > 0 && kc < 32) {
-                    n_fb = run_tc(f1, n_fb, 32, k0, kp, fb2, cnt + 1, false);
-                    f1 = fb2;
-                }
-                total_exact += n_fb;
-                if (n_fb > 0) {
-                    const int tc_splits = S.n_splits;
-                    run_exact(f1, n_fb, false, k0, k0 + kp);
-                    S.n_splits = tc_splits;  // report the splits of the main kernel, not of the re-rank
-                }
+        // ---------------- chunk pipeline
+        int64_t chunk = n_rows;
+        if (!in_dev && use_tc) {
+            const int64_t wave = (int64_t)(E->sm_count / 2) * 256;  // subject rows one wave of CTA pairs works on
+            int64_t want = 8 * wave;
+            if (const char* env = getenv("B200_CHUNK_ROWS")) want = std::max<int64_t>(256, atoll(env));  // test hook
+            if (n_rows >= 2 * want) chunk = want;
+        }
+        const int64_t n_chunks = (n_rows + chunk - 1) / chunk;
+        cudaStream_t cs = n_chunks > 1 ? E->cs : st;
+        S.n_chunks = (int32_t)n_chunks;
+        if (n_chunks > 1) {
+            CK(cudaEventRecord(E->evp[2], st));  // the copy stream starts after everything queued so far (whitelist, ...)
+            CK(cudaStreamWaitEvent(cs, E->evp[2], 0));
+        }
+        stage_rows(0, std::min(chunk, n_rows), cs);
+        CK(cudaEventRecord(E->evp[0], cs));
+        CK(cudaEventRecord(E->ev[1], cs));
+        for (int64_t c = 0; c < n_chunks; ++c) {
+            const int64_t r0 = c * chunk, r1 = std::min(n_rows, r0 + chunk);
+            if (c + 1 < n_chunks) {
+                stage_rows(r1, std::min(n_rows, r1 + chunk), cs);
+                CK(cudaEventRecord(E->evp[(c + 1) & 1], cs));
             }
-            S.n_fallback_rows = total_fb;
-            S.n_exact_rows = total_exact;
+            if (n_chunks > 1) CK(cudaStreamWaitEvent(st, E->evp[c & 1], 0));
+            compute_rows(r1 - r0, (sub32 && !rowmap) ? sub32 + r0 * d : sub32, rowmap ? rowmap + r0 : nullptr, indptr ? indptr + r0 : nullptr,
+                         o_ids + r0 * k_out, o_scores + r0 * k_out, o_counts + r0);
+            if (c + 1 == n_chunks) CK(cudaEventRecord(E->ev[4], st));
+            if (!out_dev) {
+                if (n_chunks > 1) {
+                    CK(cudaEventRecord(E->evp[2], st));
+                    CK(cudaStreamWaitEvent(cs, E->evp[2], 0));
+                }
+                CK(cudaMemcpyAsync(q->out_ids + r0 * k_out, o_ids + r0 * k_out, sizeof(int32_t) * (r1 - r0) * k_out, cudaMemcpyDeviceToHost, cs));
+                CK(cudaMemcpyAsync(q->out_scores + r0 * k_out, o_scores + r0 * k_out, sizeof(float) * (r1 - r0) * k_out, cudaMemcpyDeviceToHost, cs));
+                CK(cudaMemcpyAsync(q->out_counts + r0, o_counts + r0, sizeof(int32_t) * (r1 - r0), cudaMemcpyDeviceToHost, cs));
+                S.d2h_bytes += (int64_t)((r1 - r0) * k_out * 8 + (r1 - r0) * 4);
+            }
         }
-
-        // ---------------- results back
-        if (E->id_offset != 0) {
-            add_offset_kernel<<<grid_for(n_rows * k_out, 256), 256, 0, st>>>(o_ids, n_rows * k_out, (int32_t)E->id_offset);
-            CK(cudaGetLastError());
-            S.n_launches++;
-        }
-        CK(cudaEventRecord(E->ev[4], st));
-        if (!out_dev) {
-            CK(cudaMemcpyAsync(q->out_ids, o_ids, sizeof(int32_t) * n_rows * k_out, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(q->out_scores, o_scores, sizeof(float) * n_rows * k_out, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(q->out_counts, o_counts, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, st));
-            S.d2h_bytes = (int64_t)(n_rows * k_out * 8 + n_rows * 4);
+        if (n_chunks > 1) {  // the main stream (and through it the caller) sees the copies of the last chunks
+            CK(cudaEventRecord(E->evp[2], cs));
+            CK(cudaStreamWaitEvent(st, E->evp[2], 0));
         }
         CK(cudaEventRecord(E->ev[5], st));
         if (user && out_dev) {
@@ -907,9 +1007,8 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         }
         CK(cudaStreamSynchronize(st));
         CK(cudaEventElapsedTime(&S.ms_total, E->ev[0], E->ev[5]));
-        CK(cudaEventElapsedTime(&S.ms_h2d, E->ev[0], E->ev[1]));
-        CK(cudaEventElapsedTime(&S.ms_main, E->ev[2], E->ev[3]));
-        CK(cudaEventElapsedTime(&S.ms_d2h, E->ev[4], E->ev[5]));
+        CK(cudaEventElapsedTime(&S.ms_h2d, E->ev[0], E->ev[1]));  // exposed part: the first chunk's inputs
+        CK(cudaEventElapsedTime(&S.ms_d2h, E->ev[4], E->ev[5]));  // exposed part: the last chunk's results
     } catch (const CudaError& ce) {
         return fail(ce.e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "b200_rank_topk: %s failed at line %d: %s", ce.what,
                     ce.line, cudaGetErrorString(ce.e));

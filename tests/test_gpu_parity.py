@@ -378,3 +378,37 @@ def test_merge_matches_unsharded(rb):
     np.testing.assert_array_equal(o_ids.cpu().numpy(), ids_full)
     np.testing.assert_array_equal(o_sc.cpu().numpy(), sc_full)
     np.testing.assert_array_equal(o_cnt.cpu().numpy(), cnt_full)
+
+
+@pytest.mark.parametrize("with_ids", [False, True])
+def test_chunked_copy_compute_pipeline_matches_unchunked(rb, monkeypatch, with_ids):
+    """Large host-buffer calls are staged / ranked / copied back in row chunks on two streams (B200_CHUNK_ROWS forces small
+    chunks here): same arrays as the one-shot call, including a ragged last chunk, a CSR filter and a whitelist."""
+    from rectools_b200 import _lib
+
+    n_users, n_items, d, k = 9_001, 20_000, 64, 10
+    u, i = synth_factors(n_users, n_items, d, seed=5)
+    csr = synth_viewed_csr(n_users, n_items, 40)
+    wl = np.arange(0, n_items, 3, dtype=np.int32)
+    eng = rb.Engine(i, cosine=False)
+    sids = np.random.default_rng(0).permutation(n_users).astype(np.int64)
+
+    def call():
+        if with_ids:
+            sub = csr[sids]
+            return eng.topk(k, subjects=u, subject_ids=sids, indptr=sub.indptr, indices=sub.indices, whitelist=wl, flags=_lib.Q_FORCE_TC)
+        return eng.topk(k, subjects=u, indptr=csr.indptr, indices=csr.indices, whitelist=wl, flags=_lib.Q_FORCE_TC)
+
+    ids0, sc0, cnt0 = call()
+    assert eng.last_stats["n_chunks"] == 1
+    monkeypatch.setenv("B200_CHUNK_ROWS", "2048")
+    ids1, sc1, cnt1 = call()
+    assert eng.last_stats["n_chunks"] == 5 and eng.last_stats["path"] == 1
+    np.testing.assert_array_equal(ids0, ids1)
+    np.testing.assert_array_equal(sc0, sc1)
+    np.testing.assert_array_equal(cnt0, cnt1)
+    rows = sids if with_ids else np.arange(n_users)
+    sel = np.arange(0, n_users, 37)
+    _, oid, osc = rank_oracle("dot", u, i, rows[sel], k, csr[rows[sel]], wl, accum="f64")
+    np.testing.assert_array_equal(ids1[sel].reshape(-1), oid)
+    np.testing.assert_allclose(sc1[sel].reshape(-1), osc, rtol=3e-7, atol=1e-9)
