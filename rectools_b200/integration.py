@@ -93,10 +93,15 @@ class B200TorchRanker(B200Ranker):
 
 
 _ORIGINALS: tp.Dict[str, tp.Any] = {}
+_FAST_KEY = "VectorModel.recommend"
 
 
-def install(device: int = 0, tc_mode: str = "auto") -> None:
-    """Route `VectorModel` (ALS / PureSVD / LightFM / BPR / DSSM) and `EASEModel` ranking through the B200 engine."""
+def install(device: int = 0, tc_mode: str = "auto", fast_recommend: bool = True) -> None:
+    """Route `VectorModel` (ALS / PureSVD / LightFM / BPR / DSSM) and `EASEModel` ranking through the B200 engine.
+
+    `fast_recommend`: also give `VectorModel` the vectorised `recommend()` of `rectools_b200.recommend` (cached viewed-items
+    CSR, id maps by array indexing, no per-user Python loop); warm / cold targets and context models still go through
+    `ModelBase.recommend` (rectools/models/base.py:385-519)."""
     import importlib
 
     B200ImplicitRanker.default_device = device
@@ -106,11 +111,33 @@ def install(device: int = 0, tc_mode: str = "auto") -> None:
         if modname not in _ORIGINALS:
             _ORIGINALS[modname] = mod.ImplicitRanker
         mod.ImplicitRanker = B200ImplicitRanker
+    if fast_recommend and _FAST_KEY not in _ORIGINALS:
+        from rectools.models.base import ModelBase
+        from rectools.models.vector import VectorModel
+
+        from .recommend import recommend as fast
+
+        def _recommend(self, users, dataset, k, filter_viewed, items_to_recommend=None, add_rank_col=True,
+                       on_unsupported_targets="raise", context=None):
+            return fast(self, users, dataset, k, filter_viewed, items_to_recommend, add_rank_col, on_unsupported_targets, context,
+                        reference_recommend=lambda *a, **kw: ModelBase.recommend(self, *a, **kw))
+
+        _recommend.__doc__ = ModelBase.recommend.__doc__
+        _ORIGINALS[_FAST_KEY] = VectorModel.__dict__.get("recommend")  # None: inherited from ModelBase
+        VectorModel.recommend = _recommend
 
 
 def uninstall() -> None:
     import importlib
 
+    if _FAST_KEY in _ORIGINALS:
+        from rectools.models.vector import VectorModel
+
+        orig = _ORIGINALS.pop(_FAST_KEY)
+        if orig is None:
+            del VectorModel.recommend
+        else:
+            VectorModel.recommend = orig
     for modname, orig in list(_ORIGINALS.items()):
         importlib.import_module(modname).ImplicitRanker = orig
         del _ORIGINALS[modname]

@@ -1,0 +1,154 @@
+"""Vectorised `recommend()` around the B200 ranker: SURVEY.md section 8(f) rank 1 (the callers either side of the hot path).
+
+`ModelBase.recommend` (rectools/models/base.py:385-519) spends, around the ranker call,
+  * `Dataset.get_user_item_matrix` -- a COO -> CSR rebuild of ALL interactions on every call (vector.py:58-60,
+    dataset.py:314-348, interactions.py:162-175): ~1.3 s per 10^7 interactions;
+  * a per-user Python loop over the ranker output (rank_implicit.py:120-146), removed by `B200Ranker.rank_padded`;
+  * pandas `Series.reindex` for the internal -> external id maps (base.py:755-764, utils/indexing.py:124-132) and
+    `groupby(sort=False).cumcount()` for the rank column (base.py:778-791): ~0.15 s per 10^6 rows.
+`recommend()` below returns the same table (same columns, dtypes, row order, values) for the case every in-repo
+caller of the vector path hits -- all target users hot -- with the viewed-items CSR cached per interactions table, id maps
+applied by array indexing and the rank column written directly; anything else (warm / cold targets, models that need a
+recommend context) is delegated to the model's own `recommend`, so behaviour is never narrower than the reference's.
+
+Works on any object with the `VectorModel` surface (`_get_u2i_vectors`, `u2i_dist`, the `ModelBase` helper methods); the
+only rectools import is lazy (column names), so the module imports without rectools installed.
+"""
+from __future__ import annotations
+
+import typing as tp
+import weakref
+
+import numpy as np
+
+from .ranker import Distance, _as_distance
+
+USER_COL, ITEM_COL, SCORE_COL, RANK_COL = "user_id", "item_id", "score", "rank"  # rectools/columns.py:21-27
+
+_CSR_CACHE: "tp.Dict[int, tp.Tuple[tp.Any, tp.Any]]" = {}
+
+
+def viewed_csr(dataset: tp.Any) -> tp.Any:
+    """`dataset.get_user_item_matrix(include_weights=False)` (vector.py:59), built once per interactions table.
+
+    The reference rebuilds this CSR from the interactions DataFrame on every `recommend()` call; it only depends on that
+    (immutable by convention) table, so it is cached by the table's identity and dropped when the table is collected."""
+    df = dataset.interactions.df
+    key = id(df)
+    hit = _CSR_CACHE.get(key)
+    if hit is not None and hit[0]() is df:
+        return hit[1]
+    csr = dataset.get_user_item_matrix(include_weights=False)
+    if not csr.has_sorted_indices:
+        csr.sort_indices()
+    try:
+        ref = weakref.ref(df, lambda _r, key=key: _CSR_CACHE.pop(key, None))
+    except TypeError:  # not weak-referenceable: do not cache
+        return csr
+    _CSR_CACHE[key] = (ref, csr)
+    return csr
+
+
+def clear_viewed_cache() -> None:
+    _CSR_CACHE.clear()
+
+
+def _rows_of(csr: tp.Any, user_ids: np.ndarray) -> tp.Any:
+    """`user_items[user_ids]` (vector.py:60) without the copy when the targets are all users in order."""
+    n = csr.shape[0]
+    if len(user_ids) == n and (n == 0 or (user_ids[0] == 0 and user_ids[-1] == n - 1 and (np.diff(user_ids) == 1).all())):
+        return csr
+    return csr[user_ids]
+
+
+def finalize_scores(ranker: tp.Any, subject_ids: np.ndarray, scores: np.ndarray) -> np.ndarray:
+    """Distance post-scaling of `_process_implicit_scores` (rank_implicit.py:132-140) on the padded [n, k] array."""
+    dist = _as_distance(ranker.distance)
+    if dist == Distance.COSINE:
+        return (scores / ranker.subjects_norms[subject_ids][:, None]).astype(np.float32, copy=False)
+    if dist == Distance.EUCLIDEAN:
+        d2 = ranker.subjects_dots[subject_ids][:, None] - scores
+        return np.sqrt(np.maximum(d2, 0)).astype(np.float32)
+    return scores
+
+
+def reco_table(
+    user_ext: np.ndarray, item_ext: np.ndarray, scores: np.ndarray, counts: np.ndarray, k_out: int, add_rank_col: bool
+) -> tp.Any:
+    """`_make_reco_table` (base.py:778-791) from padded arrays: one row per returned pair, users in input order."""
+    import pandas as pd
+
+    full = k_out > 0 and len(counts) > 0 and int(counts.min()) == k_out
+    if k_out == 0 or len(counts) == 0:
+        users, items, sc = user_ext[:0], item_ext.reshape(-1)[:0], scores.reshape(-1)[:0]
+        ranks = np.empty(0, dtype=np.int64)
+    elif full:
+        users, items, sc = np.repeat(user_ext, k_out), item_ext.reshape(-1), scores.reshape(-1)
+        ranks = np.tile(np.arange(1, k_out + 1, dtype=np.int64), len(counts))
+    else:
+        mask = np.arange(k_out, dtype=np.int32)[None, :] < counts[:, None]
+        users, items, sc = np.repeat(user_ext, counts), item_ext[mask], scores[mask]
+        ranks = np.broadcast_to(np.arange(1, k_out + 1, dtype=np.int64), mask.shape)[mask]
+    df = pd.DataFrame({USER_COL: users, ITEM_COL: items, SCORE_COL: sc})
+    if add_rank_col:
+        df[RANK_COL] = ranks
+    return df
+
+
+def recommend(  # pylint: disable=too-many-locals
+    model: tp.Any,
+    users: tp.Any,
+    dataset: tp.Any,
+    k: int,
+    filter_viewed: bool,
+    items_to_recommend: tp.Optional[tp.Any] = None,
+    add_rank_col: bool = True,
+    on_unsupported_targets: str = "raise",
+    context: tp.Any = None,
+    ranker_factory: tp.Optional[tp.Callable[..., tp.Any]] = None,
+    reference_recommend: tp.Optional[tp.Callable[..., tp.Any]] = None,
+) -> tp.Any:
+    """Same contract as `ModelBase.recommend` (base.py:385-519) for `VectorModel`s; see the module docstring.
+
+    `ranker_factory(distance, user_vectors, item_vectors)` defaults to `B200ImplicitRanker` (engine cached per item
+    matrix); `reference_recommend` is the bound method to delegate to (default `model.recommend`)."""
+    fallback = reference_recommend or model.recommend
+
+    def delegate() -> tp.Any:
+        return fallback(users, dataset, k, filter_viewed, items_to_recommend=items_to_recommend, add_rank_col=add_rank_col,
+                        on_unsupported_targets=on_unsupported_targets, context=context)
+
+    if context is not None or getattr(model, "require_recommend_context", False) or not hasattr(model, "_get_u2i_vectors"):
+        return delegate()
+    model._check_is_fitted()  # pylint: disable=protected-access
+    model._check_k(k)  # pylint: disable=protected-access
+    user_type = dataset.user_id_map.external_dtype
+    item_type = dataset.item_id_map.external_dtype
+    ds = model._custom_transform_dataset_u2i(dataset, users, on_unsupported_targets, None)  # pylint: disable=protected-access
+    whitelist = model._get_sorted_item_ids_to_recommend(items_to_recommend, ds)  # pylint: disable=protected-access
+    hot, warm, cold = model._split_targets_by_hot_warm_cold(users, ds, "user")  # pylint: disable=protected-access
+    hot, warm, cold = model._check_targets_are_valid(hot, warm, cold, "user", on_unsupported_targets)  # pylint: disable=protected-access
+    if np.size(warm) > 0 or np.size(cold) > 0:
+        return delegate()
+    hot = np.asarray(hot, dtype=np.int64)
+
+    csr = _rows_of(viewed_csr(ds), hot) if (filter_viewed and hot.size) else None
+    user_vectors, item_vectors = model._get_u2i_vectors(ds)  # pylint: disable=protected-access
+    if ranker_factory is None:
+        from .integration import B200ImplicitRanker
+
+        ranker_factory = B200ImplicitRanker
+    ranker = ranker_factory(model.u2i_dist, user_vectors, item_vectors)
+    if hot.size:
+        _, ids, scores, counts = ranker.rank_padded(hot, k, csr, whitelist)
+        scores = finalize_scores(ranker, hot, scores)
+    else:
+        ids = np.empty((0, 0), dtype=np.int32)
+        scores = np.empty((0, 0), dtype=np.float32)
+        counts = np.empty(0, dtype=np.int32)
+    k_out = ids.shape[1]
+    # internal -> external ids by array indexing (`IdMap.external_ids` is sorted by internal id, identifiers.py:124-126);
+    # unfilled slots (id -1, beyond `counts`) are masked out in reco_table
+    user_ext = np.asarray(ds.user_id_map.external_ids[hot], dtype=user_type)
+    item_ext = np.asarray(ds.item_id_map.external_ids[np.maximum(ids, 0)], dtype=item_type)
+    return reco_table(user_ext, item_ext, np.asarray(scores, dtype=np.float32), counts, k_out, add_rank_col)

@@ -17,3 +17,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def rb():
+    import rectools_b200
+
+    return rectools_b200

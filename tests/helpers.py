@@ -79,3 +79,117 @@ def assert_same_ranking(ids, scores, ref_ids, ref_scores, rtol=2e-5, atol=2e-6, 
         # the item the reference put here must sit at a neighbouring position with an (almost) equal score
         assert abs(scores[p] - ref_scores[p]) <= tie_tol * scale, f"{msg}: non-tie mismatch at {p}"
     return len(bad)
+
+
+class OracleRanker:
+    """CPU stand-in with the `B200Ranker` surface the host code uses (`rank`, `rank_padded`), backed by the oracle.  Test
+    infrastructure only: it lets the host-side logic around the ranker be checked against the reference without a GPU."""
+
+    def __init__(self, distance, subjects_factors, objects_factors, num_threads=0, use_gpu=False):  # pylint: disable=unused-argument
+        self.distance = "dot"  # the oracle returns final scores (COSINE / EUCLIDEAN post-scaling included)
+        self._dist = str(getattr(distance, "value", distance))
+        self._u = np.asarray(subjects_factors, dtype=np.float32)
+        self._i = np.asarray(objects_factors, dtype=np.float32)
+
+    def rank(self, subject_ids, k=None, filter_pairs_csr=None, sorted_object_whitelist=None):
+        from oracle.topk_oracle import rank_oracle
+
+        return rank_oracle(self._dist, self._u, self._i, subject_ids, k, filter_pairs_csr, sorted_object_whitelist, accum="f32")
+
+    def rank_padded(self, subject_ids, k=None, filter_pairs_csr=None, sorted_object_whitelist=None, flags=0):  # pylint: disable=unused-argument
+        subject_ids = np.asarray(subject_ids, dtype=np.int64)
+        n_pos = self._i.shape[0] if sorted_object_whitelist is None else len(sorted_object_whitelist)
+        k_out = min(n_pos if k is None else k, n_pos)
+        ids = np.full((len(subject_ids), k_out), -1, dtype=np.int32)
+        scores = np.full((len(subject_ids), k_out), -np.finfo(np.float32).max, dtype=np.float32)
+        counts = np.zeros(len(subject_ids), dtype=np.int32)
+        for r, sid in enumerate(subject_ids):
+            csr = filter_pairs_csr[r] if filter_pairs_csr is not None else None
+            _, oi, os_ = self.rank([sid], k, csr, sorted_object_whitelist)
+            counts[r] = len(oi)
+            ids[r, : len(oi)] = oi
+            scores[r, : len(oi)] = os_
+        return subject_ids, ids, scores, counts
+
+
+class FakeIdMap:
+    """The part of `rectools.dataset.IdMap` (identifiers.py:40-126) the vectorised recommend() touches."""
+
+    def __init__(self, external_ids):
+        self.external_ids = np.asarray(external_ids)
+        self._to_internal = {e: i for i, e in enumerate(self.external_ids.tolist())}
+
+    @property
+    def external_dtype(self):
+        return self.external_ids.dtype
+
+    @property
+    def size(self):
+        return self.external_ids.size
+
+
+class _Table:  # stands in for the interactions DataFrame (cache key; must be weak-referenceable)
+    pass
+
+
+class FakeDataset:
+    """`rectools.dataset.Dataset` surface used by `rectools_b200.recommend` (dataset.py:314-348)."""
+
+    def __init__(self, user_ext, item_ext, ui_csr):
+        from types import SimpleNamespace
+
+        self.user_id_map, self.item_id_map = FakeIdMap(user_ext), FakeIdMap(item_ext)
+        self.interactions = SimpleNamespace(df=_Table())
+        self._csr = ui_csr
+        self.n_hot_users = ui_csr.shape[0]
+        self.n_matrix_builds = 0
+
+    def get_user_item_matrix(self, include_weights=True):  # pylint: disable=unused-argument
+        self.n_matrix_builds += 1
+        return self._csr.copy()
+
+
+class FakeVectorModel:
+    """`VectorModel` / `ModelBase` surface used by `rectools_b200.recommend` (base.py:652-733, vector.py:50-79, :136-150)."""
+
+    require_recommend_context = False
+
+    def __init__(self, u2i_dist, user_vectors, item_vectors):
+        self.u2i_dist, self._u, self._i = u2i_dist, user_vectors, item_vectors
+
+    def _check_is_fitted(self):
+        pass
+
+    @staticmethod
+    def _check_k(k):
+        if k <= 0:
+            raise ValueError("`k` must be positive integer")
+
+    @staticmethod
+    def _custom_transform_dataset_u2i(dataset, users, on_unsupported_targets, context=None):  # pylint: disable=unused-argument
+        return dataset
+
+    @staticmethod
+    def _get_sorted_item_ids_to_recommend(items_to_recommend, dataset):
+        if items_to_recommend is None:
+            return None
+        m = dataset.item_id_map._to_internal  # pylint: disable=protected-access
+        return np.unique([m[i] for i in np.asarray(items_to_recommend).tolist() if i in m])
+
+    @staticmethod
+    def _split_targets_by_hot_warm_cold(targets, dataset, entity):  # pylint: disable=unused-argument
+        m = dataset.user_id_map._to_internal  # pylint: disable=protected-access
+        t = np.asarray(targets).tolist()
+        known = np.asarray([m[x] for x in t if x in m], dtype=np.int64)
+        cold = np.asarray([x for x in t if x not in m])
+        return known[known < dataset.n_hot_users], known[known >= dataset.n_hot_users], cold
+
+    @staticmethod
+    def _check_targets_are_valid(hot, warm, cold, entity, on_unsupported_targets):  # pylint: disable=unused-argument
+        return hot, warm, cold
+
+    def _get_u2i_vectors(self, dataset):  # pylint: disable=unused-argument
+        return self._u, self._i
+
+    def recommend(self, *args, **kwargs):
+        raise AssertionError("the vectorised path should not have delegated")

@@ -1,0 +1,109 @@
+"""CPU: the vectorised `recommend()` returns the same table as the unmodified reference
+`ModelBase.recommend` (rectools/models/base.py:385-519).  The reference runs here through `oracle/implicit_stub`; the
+B200 ranker is replaced by the oracle-backed stand-in (`tests/helpers.OracleRanker`), so only the host logic is compared.
+Needs the reference checkout (build container only; skipped on the GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "implicit_stub")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "rectools")), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def fitted():
+    sys.path[:0] = [REF, os.path.abspath(STUB)]
+    import pandas as pd
+    from rectools import Columns
+    from rectools.dataset import Dataset
+    from rectools.models import PureSVDModel
+
+    rng = np.random.default_rng(0)
+    n_users, n_items, n_inter = 300, 120, 6000
+    df = pd.DataFrame(
+        {
+            Columns.User: rng.integers(0, n_users, n_inter) * 7 + 1000,  # external ids != internal ids
+            Columns.Item: rng.integers(0, n_items, n_inter) * 3 + 5,  # (string ids trip the reference itself under pandas 3)
+            Columns.Weight: 1.0,
+            Columns.Datetime: pd.Timestamp("2024-01-01"),
+        }
+    ).drop_duplicates([Columns.User, Columns.Item])
+    dataset = Dataset.construct(df)
+    model = PureSVDModel(factors=8, random_state=0).fit(dataset)
+    yield model, dataset, df
+    for m in [k for k in sys.modules if k.startswith("rectools.") or k == "rectools" or k.startswith("implicit")]:
+        sys.modules.pop(m, None)
+    for p_ in (REF, os.path.abspath(STUB)):
+        if p_ in sys.path:
+            sys.path.remove(p_)
+
+
+def _same(ref, got):
+    import pandas as pd
+
+    pd.testing.assert_frame_equal(ref.reset_index(drop=True), got.reset_index(drop=True), check_exact=False, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("filter_viewed", [True, False])
+@pytest.mark.parametrize("add_rank_col", [True, False])
+def test_all_users_match_reference(fitted, filter_viewed, add_rank_col):
+    from rectools_b200.recommend import recommend
+    from tests.helpers import OracleRanker
+
+    model, dataset, _ = fitted
+    users = dataset.user_id_map.external_ids
+    ref = model.recommend(users, dataset, k=7, filter_viewed=filter_viewed, add_rank_col=add_rank_col)
+    got = recommend(model, users, dataset, 7, filter_viewed, add_rank_col=add_rank_col, ranker_factory=OracleRanker)
+    assert list(ref.columns) == list(got.columns) and [str(t) for t in ref.dtypes] == [str(t) for t in got.dtypes]
+    _same(ref, got)
+
+
+def test_user_subset_whitelist_and_ragged_rows(fitted):
+    from rectools_b200.recommend import recommend
+    from tests.helpers import OracleRanker
+
+    model, dataset, df = fitted
+    rng = np.random.default_rng(1)
+    users = rng.permutation(dataset.user_id_map.external_ids)[:57]
+    # a whitelist smaller than k plus the viewed filter: users get fewer than k rows (rank_implicit.py:107-118)
+    items = df["item_id"].value_counts().index[:4].to_numpy()
+    ref = model.recommend(users, dataset, k=6, filter_viewed=True, items_to_recommend=items)
+    got = recommend(model, users, dataset, 6, True, items_to_recommend=items, ranker_factory=OracleRanker)
+    assert len(ref) < 57 * 4 + 1 and ref.groupby("user_id").size().min() < 4
+    _same(ref, got)
+    # second call: the viewed-items CSR comes from the cache
+    from rectools_b200 import recommend as rmod
+
+    assert id(dataset.interactions.df) in sys.modules[rmod.__module__]._CSR_CACHE  # pylint: disable=protected-access
+    _same(ref, recommend(model, users, dataset, 6, True, items_to_recommend=items, ranker_factory=OracleRanker))
+
+
+def test_cold_targets_are_delegated(fitted):
+    from rectools_b200.recommend import recommend
+    from tests.helpers import OracleRanker
+
+    model, dataset, _ = fitted
+    users = np.concatenate([dataset.user_id_map.external_ids[:5], [10**9]])
+    with pytest.raises(ValueError):
+        recommend(model, users, dataset, 3, True, ranker_factory=OracleRanker)
+    ref = model.recommend(users, dataset, k=3, filter_viewed=True, on_unsupported_targets="ignore")
+    got = recommend(model, users, dataset, 3, True, on_unsupported_targets="ignore", ranker_factory=OracleRanker)
+    _same(ref, got)
+
+
+def test_install_patches_vector_model_recommend(fitted):
+    import rectools.models.vector as vector
+    from rectools.models.base import ModelBase
+
+    import rectools_b200
+
+    rectools_b200.install(fast_recommend=True)
+    try:
+        assert "recommend" in vector.VectorModel.__dict__
+    finally:
+        rectools_b200.uninstall()
+    assert "recommend" not in vector.VectorModel.__dict__ and vector.VectorModel.recommend is ModelBase.recommend
