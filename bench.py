@@ -70,7 +70,13 @@ class ClockSampler:
     )
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.proc, self.first = device, [], None, 0
+
+    def mark(self):
+        """Samples taken before this call (warm-up) are not reported.  The sampler is started BEFORE the warm-up because
+        nvidia-smi's start-up (NVML initialisation over every GPU of the box) can stall CUDA calls of this process for tens
+        of milliseconds -- measured as a one-off gap inside the first timed step when it was started right before it."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -97,7 +103,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             if len(r) < 7:
                 continue
             try:
@@ -310,28 +316,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms_log = []
+
     def timed(fn, warmup, steps):
         for _ in range(warmup):
             fn()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            ev[i + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ms = torch.tensor([ev[0].elapsed_time(ev[steps])], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        step_ms_log.append([round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)])  # this rank's per-step times
         return float(ms.item())
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(a.warmup, 3) if a.steps > 0 else 0):
         step_resident()
     launches[0] = 0
     stats_log.clear()
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     total_ms = timed(step_resident, 0, a.steps)
     clocks = sampler.stop() if rank == 0 else None
     timed_launches = launches[0]
@@ -462,6 +472,7 @@ def main():
         },
         "e2e": e2e,
         "gpu_launches": int(timed_launches),
+        "ms_steps_rank0": step_ms_log[0] if step_ms_log else None,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,

@@ -100,7 +100,9 @@ typedef struct b200_rank_query {
     int32_t* out_ids;
     float* out_scores;
     int32_t* out_counts; /* [n_rows] */
-    void* stream;        /* cudaStream_t to order against when device pointers are used; NULL = engine stream */
+    void* stream;        /* cudaStream_t the device buffers are produced / consumed on; the call is ordered after the work
+                          * queued on it and it waits for the results.  NULL = the (legacy) default stream.  Ignored when
+                          * every buffer is a host buffer. */
 } b200_rank_query;
 
 typedef struct b200_rank_stats {

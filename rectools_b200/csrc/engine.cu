@@ -482,6 +482,10 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         CK(cudaSetDevice(E->device));
         cudaStream_t st = E->st;
         cudaStream_t user = reinterpret_cast<cudaStream_t>(q->stream);
+        // device pointers + NULL stream = CUDA's (legacy) default stream, like every CUDA API: producers / consumers of the
+        // buffers on that stream are ordered against the engine stream (torch's current stream is the default stream unless
+        // the caller switched it: without this a collective reading the outputs could overlap the next call's kernels)
+        if (!user && (in_dev || out_dev)) user = cudaStreamLegacy;
         if (user && (in_dev || out_dev)) {
             CK(cudaEventRecord(E->ev[6], user));
             CK(cudaStreamWaitEvent(st, E->ev[6], 0));
