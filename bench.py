@@ -202,6 +202,9 @@ def main():
     ap.add_argument("--parity-users", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--item-shards", type=int, default=0,
+                    help="N > 1: item shards I (a divisor of N); the ranks form I item shards x N/I user groups.  0 = N (the north-star "
+                         "scheme: every rank ranks all users against 1/N of the catalogue); 1 = plain user sharding")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
 
@@ -225,11 +228,36 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
 
-    # ---------------- synthetic inputs
-    lo, hi = shard_bounds(a.items, world)[rank]
+    # ---------------- partitioning: I item shards x Ug user groups (default I = world: item sharding, north star)
+    n_ishards = a.item_shards if a.item_shards > 0 else world
+    if world % n_ishards:
+        raise SystemExit("--item-shards must divide the number of GPUs")
+    n_ugroups = world // n_ishards
+    shard_idx, group_idx = rank % n_ishards, rank // n_ishards
+    ex_group = co_group = None  # exchange: my user group's item shards; collect: the holders of my item range
+    if world > 1 and n_ugroups > 1:
+        for g in range(n_ugroups):
+            grp = dist.new_group([g * n_ishards + s_ for s_ in range(n_ishards)])
+            if g == group_idx:
+                ex_group = grp
+        for s_ in range(n_ishards):
+            grp = dist.new_group([g * n_ishards + s_ for g in range(n_ugroups)])
+            if s_ == shard_idx:
+                co_group = grp
+    n_users_all = a.users
+    wl_name = workload_name(a)
+    per_group = -(-n_users_all // n_ugroups)
+    u0, u1 = shard_bounds(n_users_all, n_ugroups)[group_idx]
+
+    # ---------------- synthetic inputs (this rank's item range and user slice)
+    lo, hi = shard_bounds(a.items, n_ishards)[shard_idx]
     items_local = gen_factors(a.items, a.dim, 1, lo, hi)
-    users = gen_factors(a.users, a.dim, 0)
-    indptr, indices = gen_viewed(a.users, a.items, a.viewed)
+    users = gen_factors(n_users_all, a.dim, 0, u0, u1)
+    indptr, indices = gen_viewed(n_users_all, a.items, a.viewed)
+    if n_ugroups > 1:
+        indices = indices[indptr[u0] : indptr[u1]].copy()
+        indptr = (indptr[u0 : u1 + 1] - indptr[u0]).copy()
+    a.users = u1 - u0  # rows this rank ranks; n_users_all is the whole job
 
     eng = Engine(items_local, cosine=a.distance == "cosine", device=local_rank, tc_mode=a.tc, id_offset=lo)
     info = eng.info()
@@ -244,24 +272,40 @@ def main():
     o_sc = torch.empty((a.users, k_loc), dtype=torch.float32, device=dev)
     o_cnt = torch.empty((a.users,), dtype=torch.int32, device=dev)
     if world > 1:
-        g_ids = torch.empty((world, a.users, k), dtype=torch.int32, device=dev)
-        g_sc = torch.empty((world, a.users, k), dtype=torch.float32, device=dev)
-        g_cnt = torch.empty((world, a.users), dtype=torch.int32, device=dev)
-        m_ids = torch.empty((a.users, k), dtype=torch.int32, device=dev)
-        m_sc = torch.empty((a.users, k), dtype=torch.float32, device=dev)
-        m_cnt = torch.empty((a.users,), dtype=torch.int32, device=dev)
+        g_ids = torch.empty((n_ishards, a.users, k), dtype=torch.int32, device=dev)
+        g_sc = torch.empty((n_ishards, a.users, k), dtype=torch.float32, device=dev)
+        g_cnt = torch.empty((n_ishards, a.users), dtype=torch.int32, device=dev)
+        # merged rows of my user group (allocated `per_group` long: the collect all-gather needs equal slices)
+        m_ids = torch.full((per_group, k), -1, dtype=torch.int32, device=dev)
+        m_sc = torch.zeros((per_group, k), dtype=torch.float32, device=dev)
+        m_cnt = torch.zeros((per_group,), dtype=torch.int32, device=dev)
+        if n_ugroups > 1:
+            a_ids = torch.empty((n_ugroups * per_group, k), dtype=torch.int32, device=dev)
+            a_sc = torch.empty((n_ugroups * per_group, k), dtype=torch.float32, device=dev)
+            a_cnt = torch.empty((n_ugroups * per_group,), dtype=torch.int32, device=dev)
+        else:
+            a_ids, a_sc, a_cnt = m_ids, m_sc, m_cnt  # every rank already holds all rows
     lib = _lib.load()
     launches = [0]
     stats_log = []
 
     def exchange_and_merge():
         assert k_loc == k, "bench shards must hold at least k items"
-        dist.all_gather_into_tensor(g_ids.view(world * a.users, k), o_ids)
-        dist.all_gather_into_tensor(g_sc.view(world * a.users, k), o_sc)
-        dist.all_gather_into_tensor(g_cnt.view(world * a.users), o_cnt)
-        _lib.check(lib.b200_rank_merge(local_rank, torch.cuda.current_stream().cuda_stream, world, a.users, k, g_ids.data_ptr(),
-                                       g_sc.data_ptr(), g_cnt.data_ptr(), m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr()))
-        launches[0] += 1 + (k + 31) // 32
+        if n_ishards > 1:
+            dist.all_gather_into_tensor(g_ids.view(n_ishards * a.users, k), o_ids, group=ex_group)
+            dist.all_gather_into_tensor(g_sc.view(n_ishards * a.users, k), o_sc, group=ex_group)
+            dist.all_gather_into_tensor(g_cnt.view(n_ishards * a.users), o_cnt, group=ex_group)
+            _lib.check(lib.b200_rank_merge(local_rank, torch.cuda.current_stream().cuda_stream, n_ishards, a.users, k, g_ids.data_ptr(),
+                                           g_sc.data_ptr(), g_cnt.data_ptr(), m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr()))
+            launches[0] += 1 + (k + 31) // 32
+        else:
+            m_ids[: a.users].copy_(o_ids)
+            m_sc[: a.users].copy_(o_sc)
+            m_cnt[: a.users].copy_(o_cnt)
+        if n_ugroups > 1:  # every rank receives the rows of the other user groups
+            dist.all_gather_into_tensor(a_ids, m_ids, group=co_group)
+            dist.all_gather_into_tensor(a_sc, m_sc, group=co_group)
+            dist.all_gather_into_tensor(a_cnt, m_cnt, group=co_group)
 
     def step_resident():
         st = eng.topk_ptrs(
@@ -284,8 +328,8 @@ def main():
         h_sc = torch.empty((a.users, k_loc), dtype=torch.float32).pin_memory()
         h_cnt = torch.empty((a.users,), dtype=torch.int32).pin_memory()
         if world > 1:
-            hm_ids = torch.empty((a.users, k), dtype=torch.int32).pin_memory()
-            hm_sc = torch.empty((a.users, k), dtype=torch.float32).pin_memory()
+            hm_ids = torch.empty(tuple(a_ids.shape), dtype=torch.int32).pin_memory()
+            hm_sc = torch.empty(tuple(a_sc.shape), dtype=torch.float32).pin_memory()
     e2e_bytes = [0, 0]
     e2e_stats = {}
 
@@ -302,9 +346,9 @@ def main():
             )
             exchange_and_merge()
             if rank == 0:
-                hm_ids.copy_(m_ids, non_blocking=True)
-                hm_sc.copy_(m_sc, non_blocking=True)
-                st = dict(st, d2h_bytes=a.users * k * 8)
+                hm_ids.copy_(a_ids, non_blocking=True)
+                hm_sc.copy_(a_sc, non_blocking=True)
+                st = dict(st, d2h_bytes=int(a_ids.shape[0]) * k * 8)
             torch.cuda.current_stream().synchronize()
         e2e_bytes[0], e2e_bytes[1] = st["h2d_bytes"], st["d2h_bytes"]
         e2e_stats.clear()
@@ -346,14 +390,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     timed_launches = launches[0]
     timed_stats = list(stats_log)
-    value = a.users * a.steps / (total_ms / 1e3)
+    value = n_users_all * a.steps / (total_ms / 1e3)  # whole job: all user groups
 
     e2e = None
     if not a.no_e2e:
         e2e_steps = max(1, min(a.steps, 3))
         e2e_ms = timed(step_e2e, 1, e2e_steps)
         e2e = {
-            "value": a.users * e2e_steps / (e2e_ms / 1e3), "unit": "users/s", "steps": e2e_steps,
+            "value": n_users_all * e2e_steps / (e2e_ms / 1e3), "unit": "users/s", "steps": e2e_steps,
             "h2d_bytes_per_step": int(e2e_bytes[0]), "d2h_bytes_per_step": int(e2e_bytes[1]),
             "api": "rectools_b200.Engine.topk (C ABI b200_rank_topk) with pinned host buffers",
             "engine_ms_last_step": dict(e2e_stats),
@@ -410,15 +454,19 @@ def main():
 
     # ---------------- parity sample against the fp64 oracle, same run
     parity = None
-    if a.parity_users > 0 and world == 1:
+    if a.parity_users > 0:
         from oracle.topk_oracle import rank_oracle
         from scipy import sparse
 
-        sel = np.linspace(0, a.users - 1, a.parity_users).astype(np.int64)
+        # N > 1: rank 0 checks the merged result of (a sample of) its own user slice against the WHOLE catalogue
+        n_par = a.parity_users if world == 1 else min(a.parity_users, 64)
+        sel = np.linspace(0, a.users - 1, n_par).astype(np.int64)
         csr = sparse.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(a.users, a.items))[sel]
-        _, oid, osc = rank_oracle(a.distance, users, items_local, sel, k, csr, accum="f64")
-        got_ids = o_ids.cpu().numpy()[sel].reshape(-1)
-        got_sc = o_sc.cpu().numpy()[sel].reshape(-1)
+        items_all = items_local if world == 1 else gen_factors(a.items, a.dim, 1)
+        _, oid, osc = rank_oracle(a.distance, users, items_all, sel, k, csr, accum="f64")
+        res_ids, res_sc = (o_ids, o_sc) if world == 1 else (a_ids, a_sc)  # (rank 0 = user group 0: its rows come first)
+        got_ids = res_ids.cpu().numpy()[sel].reshape(-1)
+        got_sc = res_sc.cpu().numpy()[sel].reshape(-1)
         if a.distance == "cosine":
             un = np.sqrt(np.einsum("ij,ij->i", users[sel], users[sel], dtype=np.float64)).astype(np.float32)
             osc = osc * np.repeat(un, k)
@@ -462,8 +510,13 @@ def main():
         + " tensor-core candidates + f64-accumulated f32 re-score",
         "data": "synthetic",
         "config": {
-            "workload": workload_name(a),
-            "parallelism": f"items sharded over {world} GPU(s), NCCL all-gather + merge" if world > 1 else "single GPU",
+            "workload": wl_name,
+            "parallelism": (
+                "single GPU" if world == 1 else
+                f"items sharded over {world} GPU(s), NCCL all-gather + merge" if n_ugroups == 1 else
+                f"users sharded over {world} GPU(s), NCCL all-gather of the results" if n_ishards == 1 else
+                f"grid: {n_ishards} item shards x {n_ugroups} user groups, NCCL all-gather + merge per user group, all-gather of the results"
+            ),
             "l2": "inputs larger than L2 (fp16 item shard %.0f MB + users %.0f MB per step)"
             % (n_loc * info["d_pad"] * 2 / 1e6, a.users * info["d_pad"] * 2 / 1e6),
             "engine": {kk: timed_stats[0][kk] for kk in ("path", "k_cand", "n_splits", "n_fallback_rows", "n_exact_rows")} if timed_stats else {},

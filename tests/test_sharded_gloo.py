@@ -71,7 +71,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, item_shards=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -80,7 +80,7 @@ def _worker(rank, world, port, out):
         whitelist = np.sort(np.random.default_rng(1).choice(203, 70, replace=False))
         results = {}
         for dist_name in ("dot", "cosine"):
-            ranker = ShardedB200Ranker(dist_name, u, i, local_factory=OracleShard)
+            ranker = ShardedB200Ranker(dist_name, u, i, local_factory=OracleShard, item_shards=item_shards)
             for k, filt, wl in ((5, None, None), (7, csr, None), (4, csr, whitelist), (80, None, whitelist)):
                 sids = np.arange(40)[::-1].copy()
                 res = ranker.rank(sids, k, None if filt is None else filt[sids], wl)
@@ -92,14 +92,20 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_matches_unsharded_oracle(world):
+@pytest.mark.parametrize(
+    "world, item_shards",
+    [(2, None), (3, None), (2, 1), (4, 2), (3, 1)],
+    ids=["items2", "items3", "subjects2", "grid2x2", "subjects3-ragged"],
+)
+def test_sharded_matches_unsharded_oracle(world, item_shards):
+    """Item sharding (north star), subject sharding and the item x subject grid all return the unsharded result on every
+    rank: shard ranges, global ids, whitelist split, short shards, ragged subject slices, both all-gathers, the merge."""
     from oracle.topk_oracle import rank_oracle
 
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out, item_shards)) for r in range(world)]
     for p in procs:
         p.start()
     results = out.get(timeout=120)
