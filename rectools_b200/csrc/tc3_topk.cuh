@@ -11,9 +11,10 @@
 //   * scans the whole 128-column slice against the row threshold with ONE vote per tile;
 //   * on a hit only EXTRACTS it (column mask, value select) into a small per-thread FIFO in shared memory; the
 //     expensive part -- re-check against the current threshold, filter_pairs_csr lookup, insertion into the row's
-//     candidate list -- runs as ONE bounded step per tile for the oldest pending hit of all 32 rows of the warp at once,
-//     and the CSR lookup never waits for memory: a row's viewed ids are read through a four-entry window whose loads
-//     are issued one step (= one tile) before they are needed (measured: draining whole FIFOs at once, or advancing the
+//     candidate list -- runs as single bounded steps (the oldest pending hit of all 32 rows of the warp at once, at most
+//     one step per tile, by default every 16th tile or as soon as some row has four hits waiting: batching the steps is
+//     worth 7 %), and the CSR lookup never waits for memory: a row's viewed ids are read through a four-entry window
+//     whose loads are issued one step before they are needed (measured: draining whole FIFOs at once, or advancing the
 //     CSR cursors one row after the other, stalls the accumulator hand-over for tens of tile times);
 //   * keeps per-tile bookkeeping incremental (tile index, accumulator parity, object position).
 // Deferred hits only ever see a threshold that is older (lower) than the current one, i.e. the filter is weaker, never
@@ -33,12 +34,25 @@ namespace tc {
 constexpr int T3_THREADS = 384;
 constexpr int T3_EPI0 = 4;
 constexpr int T3_REGS_LOW = 40, T3_REGS_EPI = 232;  // 32 * (40 + 2 * 232) = 16128 <= 16384 per sub-partition
+#ifndef B200_T3_ONEHIT
+#define B200_T3_ONEHIT 0  // a chunk with exactly one score above the threshold: that score is the chunk maximum (no select tree);
+                          // measured slower (the extra divergent branch costs more than the 31 selects it saves)
+#endif
+#ifndef B200_T3_STEP_LAZY
+#define B200_T3_STEP_LAZY 1  // deferred work every B200_T3_STEP_PERIOD-th tile unless some row has B200_T3_BACKLOG or more hits pending
+#endif
+#ifndef B200_T3_STEP_PERIOD
+#define B200_T3_STEP_PERIOD 16  // power of two
+#endif
+#ifndef B200_T3_BACKLOG
+#define B200_T3_BACKLOG 4
+#endif
 #ifndef B200_T3_Q
-#define B200_T3_Q 4  // measured: see profiles/r01_ab_tc3.txt
+#define B200_T3_Q 8  // measured together with the step period / backlog: profiles/r01_ab_tc3.txt
 #endif
 constexpr int T3_Q = B200_T3_Q;                    // deferred hits per thread
 constexpr int T3_QSTRIDE = 8 * 32 * 8;             // bytes between FIFO slots: [slot][epilogue thread] x (score, position)
-constexpr int T3_QBYTES = T3_Q * T3_QSTRIDE;       // 8 KiB per CTA
+constexpr int T3_QBYTES = T3_Q * T3_QSTRIDE;       // 16 KiB per CTA at 8 slots
 constexpr int T3_TN = 256, T3_HALF = 128;
 
 __device__ __forceinline__ void sts_v2(uint32_t a, float x, uint32_t y) {
@@ -169,12 +183,21 @@ __device__ __forceinline__ void window_load(const int32_t* __restrict__ indices,
 // true when some lane still has hits but no free slot: the caller runs a fifo_step and calls again with the remaining mask.
 template <int OFF>
 __device__ __forceinline__ bool chunk_push(const uint32_t (&r)[T3_HALF], unsigned& hits, uint32_t pos0, float thr, uint32_t n_pos,
-                                           uint32_t qaddr, int head, int& tail) {
+                                           uint32_t qaddr, int head, int& tail, float chunk_mx, bool one_hit) {
     while (__any_sync(B200_FULL_MASK, hits != 0)) {
         if (hits && tail - head < T3_Q) {
             const int j = __ffs(hits) - 1;
             hits &= hits - 1;
+#if B200_T3_ONEHIT
+            // the usual case in the sparse tail of the stream: the only score above the threshold IS the chunk maximum
+            float val;
+            if (one_hit)
+                val = chunk_mx;
+            else
+                val = chunk_select<OFF>(r, j);
+#else
             const float val = chunk_select<OFF>(r, j);
+#endif
             const uint32_t pos = pos0 + (uint32_t)(OFF + j);
             if (val > thr && pos < n_pos) {
                 sts_v2(qaddr + (uint32_t)(tail & (T3_Q - 1)) * T3_QSTRIDE, val, pos);
@@ -438,18 +461,27 @@ tc3_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                         if (__any_sync(B200_FULL_MASK, m1 > thr)) h1 = chunk_hits<32>(r, thr);
                         if (__any_sync(B200_FULL_MASK, m2 > thr)) h2 = chunk_hits<64>(r, thr);
                         if (__any_sync(B200_FULL_MASK, m3 > thr)) h3 = chunk_hits<96>(r, thr);
+                        // (evaluated on the complete masks: after a pop the remaining bit need not be the maximum)
+                        const bool o0 = __popc(h0) == 1, o1 = __popc(h1) == 1, o2 = __popc(h2) == 1, o3 = __popc(h3) == 1;
                         for (;;) {
-                            bool stuck = chunk_push<0>(r, h0, pos_t, rs.thr, n_pos, qaddr, head, tail);
-                            if (!stuck) stuck = chunk_push<32>(r, h1, pos_t, rs.thr, n_pos, qaddr, head, tail);
-                            if (!stuck) stuck = chunk_push<64>(r, h2, pos_t, rs.thr, n_pos, qaddr, head, tail);
-                            if (!stuck) stuck = chunk_push<96>(r, h3, pos_t, rs.thr, n_pos, qaddr, head, tail);
+                            bool stuck = chunk_push<0>(r, h0, pos_t, rs.thr, n_pos, qaddr, head, tail, m0, o0);
+                            if (!stuck) stuck = chunk_push<32>(r, h1, pos_t, rs.thr, n_pos, qaddr, head, tail, m1, o1);
+                            if (!stuck) stuck = chunk_push<64>(r, h2, pos_t, rs.thr, n_pos, qaddr, head, tail, m2, o2);
+                            if (!stuck) stuck = chunk_push<96>(r, h3, pos_t, rs.thr, n_pos, qaddr, head, tail, m3, o3);
                             if (!stuck) break;
                             fifo_step(p, rs, cw, qaddr, head, tail, ls, li, kc);  // dense phase: make room, then go on
                         }
                     }
                     // deferred work: at most one step per tile (bounded latency in front of the next accumulator), except
                     // where everything pending has to be finished
-                    if (__any_sync(B200_FULL_MASK, head != tail)) {
+#if B200_T3_STEP_LAZY
+                    // (hits wait for at most STEP_PERIOD tiles; rows with a backlog and the flush points are served at once)
+                    const bool due = (tail - head >= B200_T3_BACKLOG) ||
+                                     (head != tail && ((it & (B200_T3_STEP_PERIOD - 1)) == B200_T3_STEP_PERIOD - 1 || force || last));
+#else
+                    const bool due = head != tail;
+#endif
+                    if (__any_sync(B200_FULL_MASK, due)) {
                         fifo_step(p, rs, cw, qaddr, head, tail, ls, li, kc);
                         if (force || last)
                             while (__any_sync(B200_FULL_MASK, head != tail)) fifo_step(p, rs, cw, qaddr, head, tail, ls, li, kc);
