@@ -412,3 +412,31 @@ def test_chunked_copy_compute_pipeline_matches_unchunked(rb, monkeypatch, with_i
     _, oid, osc = rank_oracle("dot", u, i, rows[sel], k, csr[rows[sel]], wl, accum="f64")
     np.testing.assert_array_equal(ids1[sel].reshape(-1), oid)
     np.testing.assert_allclose(sc1[sel].reshape(-1), osc, rtol=3e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("cosine", [False, True])
+def test_implicit_gpu_shim_topk(rb, cosine):
+    """`rectools_b200.implicit_gpu.KnnQuery().topk` (the stand-in for `implicit.gpu.KnnQuery().topk`, call shape of
+    rank_implicit.py:175-182) against the oracle's restatement of implicit's top-k, incl. a row with fewer than k survivors."""
+    from oracle.topk_oracle import implicit_topk
+    from rectools_b200.implicit_gpu import COOMatrix, KnnQuery, Matrix
+
+    u, i = synth_factors(300, 5_000, 64, seed=11)
+    csr = synth_viewed_csr(300, 5_000, 25).tolil()
+    csr[7, :] = 1.0  # everything viewed except three items
+    csr[7, [5, 50, 500]] = 0.0
+    csr = sparse.csr_matrix(csr)
+    csr.eliminate_zeros()
+    norms = None
+    if cosine:
+        norms = np.sqrt(np.einsum("ij,ij->i", i, i, dtype=np.float64)).astype(np.float32)
+    ids, scores = KnnQuery().topk(
+        items=Matrix(i), m=Matrix(u), k=10, item_norms=None if norms is None else Matrix(norms[None, :]),
+        query_filter=COOMatrix(csr.tocoo()), item_filter=None,
+    )
+    oid, osc = implicit_topk(i, u, 10, norms, csr, accum="f64")
+    valid = osc > -1e38
+    assert ids.shape == (300, 10) and valid[7].sum() == 3 and (scores[7, 3:] <= -3.0e38).all() and (ids[7, 3:] == -1).all()
+    np.testing.assert_array_equal(ids[valid], oid[valid])
+    np.testing.assert_allclose(scores[valid], osc[valid], rtol=3e-7, atol=1e-9)
+    assert (scores[~valid] <= -3.0e38).all()
