@@ -34,10 +34,6 @@ namespace tc {
 constexpr int T3_THREADS = 384;
 constexpr int T3_EPI0 = 4;
 constexpr int T3_REGS_LOW = 40, T3_REGS_EPI = 232;  // 32 * (40 + 2 * 232) = 16128 <= 16384 per sub-partition
-#ifndef B200_T3_ONEHIT
-#define B200_T3_ONEHIT 0  // a chunk with exactly one score above the threshold: that score is the chunk maximum (no select tree);
-                          // measured slower (the extra divergent branch costs more than the 31 selects it saves)
-#endif
 #ifndef B200_T3_STEP_LAZY
 #define B200_T3_STEP_LAZY 1  // deferred work every B200_T3_STEP_PERIOD-th tile unless some row has B200_T3_BACKLOG or more hits pending
 #endif
@@ -183,21 +179,14 @@ __device__ __forceinline__ void window_load(const int32_t* __restrict__ indices,
 // true when some lane still has hits but no free slot: the caller runs a fifo_step and calls again with the remaining mask.
 template <int OFF>
 __device__ __forceinline__ bool chunk_push(const uint32_t (&r)[T3_HALF], unsigned& hits, uint32_t pos0, float thr, uint32_t n_pos,
-                                           uint32_t qaddr, int head, int& tail, float chunk_mx, bool one_hit) {
+                                           uint32_t qaddr, int head, int& tail) {
     while (__any_sync(B200_FULL_MASK, hits != 0)) {
         if (hits && tail - head < T3_Q) {
             const int j = __ffs(hits) - 1;
             hits &= hits - 1;
-#if B200_T3_ONEHIT
-            // the usual case in the sparse tail of the stream: the only score above the threshold IS the chunk maximum
-            float val;
-            if (one_hit)
-                val = chunk_mx;
-            else
-                val = chunk_select<OFF>(r, j);
-#else
+            // (taking the chunk maximum when it is the only score above the threshold, instead of the select tree, measured
+            // slower: the extra branch costs more than the 31 selects it saves)
             const float val = chunk_select<OFF>(r, j);
-#endif
             const uint32_t pos = pos0 + (uint32_t)(OFF + j);
             if (val > thr && pos < n_pos) {
                 sts_v2(qaddr + (uint32_t)(tail & (T3_Q - 1)) * T3_QSTRIDE, val, pos);
@@ -461,13 +450,11 @@ tc3_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
                         if (__any_sync(B200_FULL_MASK, m1 > thr)) h1 = chunk_hits<32>(r, thr);
                         if (__any_sync(B200_FULL_MASK, m2 > thr)) h2 = chunk_hits<64>(r, thr);
                         if (__any_sync(B200_FULL_MASK, m3 > thr)) h3 = chunk_hits<96>(r, thr);
-                        // (evaluated on the complete masks: after a pop the remaining bit need not be the maximum)
-                        const bool o0 = __popc(h0) == 1, o1 = __popc(h1) == 1, o2 = __popc(h2) == 1, o3 = __popc(h3) == 1;
                         for (;;) {
-                            bool stuck = chunk_push<0>(r, h0, pos_t, rs.thr, n_pos, qaddr, head, tail, m0, o0);
-                            if (!stuck) stuck = chunk_push<32>(r, h1, pos_t, rs.thr, n_pos, qaddr, head, tail, m1, o1);
-                            if (!stuck) stuck = chunk_push<64>(r, h2, pos_t, rs.thr, n_pos, qaddr, head, tail, m2, o2);
-                            if (!stuck) stuck = chunk_push<96>(r, h3, pos_t, rs.thr, n_pos, qaddr, head, tail, m3, o3);
+                            bool stuck = chunk_push<0>(r, h0, pos_t, rs.thr, n_pos, qaddr, head, tail);
+                            if (!stuck) stuck = chunk_push<32>(r, h1, pos_t, rs.thr, n_pos, qaddr, head, tail);
+                            if (!stuck) stuck = chunk_push<64>(r, h2, pos_t, rs.thr, n_pos, qaddr, head, tail);
+                            if (!stuck) stuck = chunk_push<96>(r, h3, pos_t, rs.thr, n_pos, qaddr, head, tail);
                             if (!stuck) break;
                             fifo_step(p, rs, cw, qaddr, head, tail, ls, li, kc);  // dense phase: make room, then go on
                         }
