@@ -11,7 +11,7 @@ The CUDA library is `rectools_b200/libb200rank.so` (C ABI: include/b200_rank.h);
 """
 from .ranker import B200Ranker, Distance, Engine, flatten_padded  # noqa: F401
 from .integration import B200ImplicitRanker, B200TorchRanker, install, uninstall  # noqa: F401
-from .recommend import recommend  # noqa: F401
+from .recommend import recommend, recommend_to_items  # noqa: F401
 
 __all__ = [
     "B200Ranker",
@@ -22,6 +22,7 @@ __all__ = [
     "flatten_padded",
     "install",
     "recommend",
+    "recommend_to_items",
     "uninstall",
 ]
 __version__ = "0.1.0"

@@ -116,15 +116,24 @@ def install(device: int = 0, tc_mode: str = "auto", fast_recommend: bool = True)
         from rectools.models.vector import VectorModel
 
         from .recommend import recommend as fast
+        from .recommend import recommend_to_items as fast_i2i
 
         def _recommend(self, users, dataset, k, filter_viewed, items_to_recommend=None, add_rank_col=True,
                        on_unsupported_targets="raise", context=None):
             return fast(self, users, dataset, k, filter_viewed, items_to_recommend, add_rank_col, on_unsupported_targets, context,
                         reference_recommend=lambda *a, **kw: ModelBase.recommend(self, *a, **kw))
 
+        def _recommend_to_items(self, target_items, dataset, k, filter_itself=True, items_to_recommend=None, add_rank_col=True,
+                                on_unsupported_targets="raise"):
+            return fast_i2i(self, target_items, dataset, k, filter_itself, items_to_recommend, add_rank_col, on_unsupported_targets,
+                            reference_recommend=lambda *a, **kw: ModelBase.recommend_to_items(self, *a, **kw))
+
         _recommend.__doc__ = ModelBase.recommend.__doc__
-        _ORIGINALS[_FAST_KEY] = VectorModel.__dict__.get("recommend")  # None: inherited from ModelBase
+        _recommend_to_items.__doc__ = ModelBase.recommend_to_items.__doc__
+        # (None: the attribute is inherited from ModelBase)
+        _ORIGINALS[_FAST_KEY] = (VectorModel.__dict__.get("recommend"), VectorModel.__dict__.get("recommend_to_items"))
         VectorModel.recommend = _recommend
+        VectorModel.recommend_to_items = _recommend_to_items
 
 
 def uninstall() -> None:
@@ -133,11 +142,11 @@ def uninstall() -> None:
     if _FAST_KEY in _ORIGINALS:
         from rectools.models.vector import VectorModel
 
-        orig = _ORIGINALS.pop(_FAST_KEY)
-        if orig is None:
-            del VectorModel.recommend
-        else:
-            VectorModel.recommend = orig
+        for name, orig in zip(("recommend", "recommend_to_items"), _ORIGINALS.pop(_FAST_KEY)):
+            if orig is None:
+                delattr(VectorModel, name)
+            else:
+                setattr(VectorModel, name, orig)
     for modname, orig in list(_ORIGINALS.items()):
         importlib.import_module(modname).ImplicitRanker = orig
         del _ORIGINALS[modname]

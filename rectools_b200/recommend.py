@@ -24,6 +24,7 @@ import numpy as np
 from .ranker import Distance, _as_distance
 
 USER_COL, ITEM_COL, SCORE_COL, RANK_COL = "user_id", "item_id", "score", "rank"  # rectools/columns.py:21-27
+TARGET_ITEM_COL = "target_item_id"  # rectools/columns.py:23
 
 _CSR_CACHE: "tp.Dict[int, tp.Tuple[tp.Any, tp.Any]]" = {}
 
@@ -73,23 +74,32 @@ def finalize_scores(ranker: tp.Any, subject_ids: np.ndarray, scores: np.ndarray)
 
 
 def reco_table(
-    user_ext: np.ndarray, item_ext: np.ndarray, scores: np.ndarray, counts: np.ndarray, k_out: int, add_rank_col: bool
+    target_ext: np.ndarray,
+    item_ext: np.ndarray,
+    scores: np.ndarray,
+    counts: np.ndarray,
+    k_out: int,
+    add_rank_col: bool,
+    target_col: str = USER_COL,
+    keep: tp.Optional[np.ndarray] = None,
 ) -> tp.Any:
-    """`_make_reco_table` (base.py:778-791) from padded arrays: one row per returned pair, users in input order."""
+    """`_make_reco_table` (base.py:778-791) from padded arrays: one row per returned pair, targets in input order.
+    `keep` (bool [n, k_out]) selects the pairs explicitly (i2i: the target itself removed); default: the first `counts`."""
     import pandas as pd
 
-    full = k_out > 0 and len(counts) > 0 and int(counts.min()) == k_out
-    if k_out == 0 or len(counts) == 0:
-        users, items, sc = user_ext[:0], item_ext.reshape(-1)[:0], scores.reshape(-1)[:0]
+    full = keep is None and k_out > 0 and len(counts) > 0 and int(counts.min()) == k_out
+    if k_out == 0 or len(target_ext) == 0:
+        targets, items, sc = target_ext[:0], item_ext.reshape(-1)[:0], scores.reshape(-1)[:0]
         ranks = np.empty(0, dtype=np.int64)
     elif full:
-        users, items, sc = np.repeat(user_ext, k_out), item_ext.reshape(-1), scores.reshape(-1)
+        targets, items, sc = np.repeat(target_ext, k_out), item_ext.reshape(-1), scores.reshape(-1)
         ranks = np.tile(np.arange(1, k_out + 1, dtype=np.int64), len(counts))
     else:
-        mask = np.arange(k_out, dtype=np.int32)[None, :] < counts[:, None]
-        users, items, sc = np.repeat(user_ext, counts), item_ext[mask], scores[mask]
-        ranks = np.broadcast_to(np.arange(1, k_out + 1, dtype=np.int64), mask.shape)[mask]
-    df = pd.DataFrame({USER_COL: users, ITEM_COL: items, SCORE_COL: sc})
+        mask = keep if keep is not None else np.arange(k_out, dtype=np.int32)[None, :] < counts[:, None]
+        per_row = mask.sum(axis=1)
+        targets, items, sc = np.repeat(target_ext, per_row), item_ext[mask], scores[mask]
+        ranks = np.cumsum(mask, axis=1, dtype=np.int64)[mask]
+    df = pd.DataFrame({target_col: targets, ITEM_COL: items, SCORE_COL: sc})
     if add_rank_col:
         df[RANK_COL] = ranks
     return df
@@ -152,3 +162,61 @@ def recommend(  # pylint: disable=too-many-locals
     user_ext = np.asarray(ds.user_id_map.external_ids[hot], dtype=user_type)
     item_ext = np.asarray(ds.item_id_map.external_ids[np.maximum(ids, 0)], dtype=item_type)
     return reco_table(user_ext, item_ext, np.asarray(scores, dtype=np.float32), counts, k_out, add_rank_col)
+
+
+def recommend_to_items(  # pylint: disable=too-many-locals
+    model: tp.Any,
+    target_items: tp.Any,
+    dataset: tp.Any,
+    k: int,
+    filter_itself: bool = True,
+    items_to_recommend: tp.Optional[tp.Any] = None,
+    add_rank_col: bool = True,
+    on_unsupported_targets: str = "raise",
+    ranker_factory: tp.Optional[tp.Callable[..., tp.Any]] = None,
+    reference_recommend: tp.Optional[tp.Callable[..., tp.Any]] = None,
+) -> tp.Any:
+    """Same contract as `ModelBase.recommend_to_items` (base.py:521-646) for `VectorModel`s: the same
+    kernel with subjects = item vectors (`_get_i2i_vectors`, `i2i_dist`), `k + 1` results when the target itself is filtered,
+    and that filter (`_filter_item_itself_from_i2i_reco`, base.py:745-753: a DataFrame query + groupby.head) done on the
+    padded arrays.  Warm / cold or repeated targets are delegated to the reference method."""
+    fallback = reference_recommend or model.recommend_to_items
+
+    def delegate() -> tp.Any:
+        return fallback(target_items, dataset, k, filter_itself=filter_itself, items_to_recommend=items_to_recommend,
+                        add_rank_col=add_rank_col, on_unsupported_targets=on_unsupported_targets)
+
+    if not hasattr(model, "_get_i2i_vectors"):
+        return delegate()
+    model._check_is_fitted()  # pylint: disable=protected-access
+    model._check_k(k)  # pylint: disable=protected-access
+    item_type = dataset.item_id_map.external_dtype
+    ds = model._custom_transform_dataset_i2i(dataset, target_items, on_unsupported_targets)  # pylint: disable=protected-access
+    whitelist = model._get_sorted_item_ids_to_recommend(items_to_recommend, ds)  # pylint: disable=protected-access
+    hot, warm, cold = model._split_targets_by_hot_warm_cold(target_items, ds, "item")  # pylint: disable=protected-access
+    hot, warm, cold = model._check_targets_are_valid(hot, warm, cold, "item", on_unsupported_targets)  # pylint: disable=protected-access
+    hot = np.asarray(hot, dtype=np.int64)
+    if np.size(warm) > 0 or np.size(cold) > 0 or len(np.unique(hot)) != len(hot):
+        return delegate()  # (the reference groups the self-filter by target id: repeated targets share one group)
+
+    requested_k = k + 1 if filter_itself else k  # base.py:603
+    vectors_1, vectors_2 = model._get_i2i_vectors(ds)  # pylint: disable=protected-access
+    if ranker_factory is None:
+        from .integration import B200ImplicitRanker
+
+        ranker_factory = B200ImplicitRanker
+    ranker = ranker_factory(model.i2i_dist, vectors_1, vectors_2)
+    if hot.size:
+        _, ids, scores, counts = ranker.rank_padded(hot, requested_k, None, whitelist)
+        scores = finalize_scores(ranker, hot, scores)
+    else:
+        ids, scores, counts = np.empty((0, 0), np.int32), np.empty((0, 0), np.float32), np.empty(0, np.int32)
+    k_out = ids.shape[1]
+    keep = np.arange(k_out, dtype=np.int32)[None, :] < counts[:, None]
+    if filter_itself and k_out:
+        keep &= ids != hot[:, None]
+        keep &= np.cumsum(keep, axis=1) <= k  # the first k of what is left (groupby("tid").head(k))
+    target_ext = np.asarray(ds.item_id_map.external_ids[hot], dtype=item_type)
+    item_ext = np.asarray(ds.item_id_map.external_ids[np.maximum(ids, 0)], dtype=item_type)
+    return reco_table(target_ext, item_ext, np.asarray(scores, dtype=np.float32), keep.sum(axis=1), k_out, add_rank_col,
+                      target_col=TARGET_ITEM_COL, keep=keep)

@@ -154,8 +154,8 @@ class FakeVectorModel:
 
     require_recommend_context = False
 
-    def __init__(self, u2i_dist, user_vectors, item_vectors):
-        self.u2i_dist, self._u, self._i = u2i_dist, user_vectors, item_vectors
+    def __init__(self, u2i_dist, user_vectors, item_vectors, i2i_dist="cosine"):
+        self.u2i_dist, self.i2i_dist, self._u, self._i = u2i_dist, i2i_dist, user_vectors, item_vectors
 
     def _check_is_fitted(self):
         pass
@@ -177,12 +177,18 @@ class FakeVectorModel:
         return np.unique([m[i] for i in np.asarray(items_to_recommend).tolist() if i in m])
 
     @staticmethod
-    def _split_targets_by_hot_warm_cold(targets, dataset, entity):  # pylint: disable=unused-argument
-        m = dataset.user_id_map._to_internal  # pylint: disable=protected-access
+    def _custom_transform_dataset_i2i(dataset, target_items, on_unsupported_targets):  # pylint: disable=unused-argument
+        return dataset
+
+    @staticmethod
+    def _split_targets_by_hot_warm_cold(targets, dataset, entity):
+        id_map = dataset.user_id_map if entity == "user" else dataset.item_id_map
+        n_hot = dataset.n_hot_users if entity == "user" else id_map.size
+        m = id_map._to_internal  # pylint: disable=protected-access
         t = np.asarray(targets).tolist()
         known = np.asarray([m[x] for x in t if x in m], dtype=np.int64)
         cold = np.asarray([x for x in t if x not in m])
-        return known[known < dataset.n_hot_users], known[known >= dataset.n_hot_users], cold
+        return known[known < n_hot], known[known >= n_hot], cold
 
     @staticmethod
     def _check_targets_are_valid(hot, warm, cold, entity, on_unsupported_targets):  # pylint: disable=unused-argument
@@ -191,5 +197,11 @@ class FakeVectorModel:
     def _get_u2i_vectors(self, dataset):  # pylint: disable=unused-argument
         return self._u, self._i
 
+    def _get_i2i_vectors(self, dataset):  # pylint: disable=unused-argument
+        return self._i, self._i
+
     def recommend(self, *args, **kwargs):
+        raise AssertionError("the vectorised path should not have delegated")
+
+    def recommend_to_items(self, *args, **kwargs):
         raise AssertionError("the vectorised path should not have delegated")

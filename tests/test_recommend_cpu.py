@@ -103,7 +103,38 @@ def test_install_patches_vector_model_recommend(fitted):
 
     rectools_b200.install(fast_recommend=True)
     try:
-        assert "recommend" in vector.VectorModel.__dict__
+        assert "recommend" in vector.VectorModel.__dict__ and "recommend_to_items" in vector.VectorModel.__dict__
     finally:
         rectools_b200.uninstall()
     assert "recommend" not in vector.VectorModel.__dict__ and vector.VectorModel.recommend is ModelBase.recommend
+    assert vector.VectorModel.recommend_to_items is ModelBase.recommend_to_items
+
+
+@pytest.mark.parametrize("filter_itself", [True, False])
+@pytest.mark.parametrize("with_whitelist", [False, True])
+def test_recommend_to_items_matches_reference(fitted, filter_itself, with_whitelist):
+    """i2i = the same ranker with item vectors as subjects, k + 1 results, self-filter on the padded arrays."""
+    from rectools_b200.recommend import recommend_to_items
+    from tests.helpers import OracleRanker
+
+    model, dataset, df = fitted
+    rng = np.random.default_rng(2)
+    targets = rng.permutation(dataset.item_id_map.external_ids)[:40]
+    wl = None
+    if with_whitelist:  # small enough that some targets get fewer than k rows; contains some of the targets themselves
+        wl = np.concatenate([targets[:3], df["item_id"].value_counts().index[:4].to_numpy()])
+    ref = model.recommend_to_items(targets, dataset, k=5, filter_itself=filter_itself, items_to_recommend=wl)
+    got = recommend_to_items(model, targets, dataset, 5, filter_itself, items_to_recommend=wl, ranker_factory=OracleRanker)
+    assert list(ref.columns) == list(got.columns) and [str(t) for t in ref.dtypes] == [str(t) for t in got.dtypes]
+    _same(ref, got)
+
+
+def test_recommend_to_items_repeated_targets_are_delegated(fitted):
+    from rectools_b200.recommend import recommend_to_items
+    from tests.helpers import OracleRanker
+
+    model, dataset, _ = fitted
+    t = dataset.item_id_map.external_ids[:3]
+    targets = np.concatenate([t, t[:1]])
+    ref = model.recommend_to_items(targets, dataset, k=4)
+    _same(ref, recommend_to_items(model, targets, dataset, 4, ranker_factory=OracleRanker))

@@ -50,3 +50,30 @@ def test_recommend_table_matches_reference_golden(rb, golden_dir):
     assert df.groupby("user_id", sort=False).size().max() <= 6
     assert (df.groupby("user_id", sort=False).cumcount().to_numpy() + 1 == df["rank"].to_numpy()).all()
     assert set(df["item_id"].unique()) <= set(wl_ext.tolist())
+
+
+def test_recommend_to_items_matches_oracle(rb, golden_dir):
+    """`recommend_to_items` = the same engine with item vectors as subjects (COSINE), k + 1, self removed."""
+    from oracle.topk_oracle import rank_oracle
+    from rectools_b200.recommend import recommend_to_items
+
+    g = np.load(os.path.join(golden_dir, "puresvd_c1.npz"))
+    items = g["item_factors"]
+    n_items = items.shape[0]
+    item_ext = np.arange(n_items, dtype=np.int64) * 3 + 7
+    dataset = FakeDataset(np.arange(4, dtype=np.int64), item_ext, sparse.csr_matrix((4, n_items), dtype=np.float32))
+    model = FakeVectorModel("dot", g["user_factors"][:4], items, i2i_dist="cosine")
+    targets = np.random.default_rng(0).permutation(n_items)[:500]
+    wl = np.sort(np.random.default_rng(1).choice(n_items, 900, replace=False))
+    for whitelist in (None, wl):
+        df = recommend_to_items(model, item_ext[targets], dataset, 10, filter_itself=True,
+                                items_to_recommend=None if whitelist is None else item_ext[whitelist])
+        assert list(df.columns) == ["target_item_id", "item_id", "score", "rank"]
+        _, oid, osc = rank_oracle("cosine", items, items, targets, 11, None, whitelist, accum="f64")
+        oid, osc = oid.reshape(len(targets), 11), osc.reshape(len(targets), 11)
+        keep = oid != targets[:, None]
+        keep &= np.cumsum(keep, axis=1) <= 10
+        np.testing.assert_array_equal(df["target_item_id"].to_numpy(), np.repeat(item_ext[targets], keep.sum(axis=1)))
+        assert_same_ranking((df["item_id"].to_numpy() - 7) // 3, df["score"].to_numpy(), oid[keep], osc[keep], tie_tol=2e-6)
+        np.testing.assert_array_equal(df["rank"].to_numpy(), np.cumsum(keep, axis=1)[keep])
+        assert not (df["target_item_id"] == df["item_id"]).any()
