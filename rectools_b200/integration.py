@@ -57,13 +57,16 @@ class B200ImplicitRanker(B200Ranker):
     def __init__(self, distance, subjects_factors, objects_factors, num_threads: int = 0, use_gpu: bool = False) -> None:
         dist = _as_distance(distance)
         engine = None
+        subjects_key = None
         if dist != Distance.EUCLIDEAN and isinstance(objects_factors, np.ndarray):
             objects = _dense_f32(objects_factors)
             engine = cached_engine(objects, dist == Distance.COSINE, self.default_device, self.default_tc_mode)
             objects_factors = objects
+            if isinstance(subjects_factors, np.ndarray) and subjects_factors.dtype == np.float32 and subjects_factors.flags.c_contiguous:
+                subjects_key = _fingerprint(subjects_factors)  # same matrix as in the previous call: stays resident
         super().__init__(
             dist, subjects_factors, objects_factors, num_threads=num_threads, use_gpu=use_gpu,
-            device=self.default_device, tc_mode=self.default_tc_mode, engine=engine,
+            device=self.default_device, tc_mode=self.default_tc_mode, engine=engine, subjects_key=subjects_key,
         )
 
 

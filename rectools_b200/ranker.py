@@ -129,11 +129,18 @@ class Engine:
         out["device_name"] = inf.device_name.decode()
         return out
 
-    def set_subjects(self, subjects: np.ndarray) -> None:
+    def set_subjects(self, subjects: np.ndarray, key: tp.Optional[tp.Hashable] = None, owner: tp.Any = None) -> None:
+        """Upload the resident subject factors.  `key` (optional identity of the matrix): a repeated call with the key of the
+        matrix that is already resident is a no-op -- `VectorModel` builds a new ranker per `recommend()` call (vector.py:66).
+        `owner`: the ranker whose subjects are resident now (several rankers may share one cached engine)."""
         subjects = np.ascontiguousarray(subjects, dtype=np.float32)
         if subjects.shape[1] != self.d:
             raise ValueError("subject and object factors must have the same number of columns")
+        self.subjects_owner = owner
+        if key is not None and key == getattr(self, "_subjects_key", None):
+            return
         _lib.check(self._lib.b200_rank_set_subjects(self._h, subjects.ctypes.data, subjects.shape[0], 0))
+        self._subjects_key = key
 
     def set_subjects_device(self, ptr: int, n_subjects: int) -> None:
         _lib.check(self._lib.b200_rank_set_subjects(self._h, ptr, n_subjects, 1))
@@ -270,6 +277,7 @@ class B200Ranker:
         device: int = 0,
         tc_mode: str = "auto",
         engine: tp.Optional[Engine] = None,
+        subjects_key: tp.Optional[tp.Hashable] = None,
     ) -> None:
         self.distance = _as_distance(distance)
         if sparse.issparse(subjects_factors) and self.distance != Distance.DOT:
@@ -286,7 +294,8 @@ class B200Ranker:
         self.n_subjects, self.n_objects = subjects.shape[0], objects.shape[0]
         subjects, objects, self.subjects_norms, self.subjects_dots = prepare_factors(self.distance, subjects, objects)
         self.engine = engine or Engine(objects, cosine=self.distance == Distance.COSINE, device=device, tc_mode=tc_mode)
-        self.engine.set_subjects(subjects)
+        self._subjects, self._subjects_key = subjects, subjects_key
+        self.engine.set_subjects(subjects, key=subjects_key, owner=self)
         self.last_stats: tp.Dict[str, tp.Any] = {}
 
     def _init_from_device_tensors(self, subjects_factors: tp.Any, objects_factors: tp.Any, tc_mode: str) -> None:
@@ -350,6 +359,9 @@ class B200Ranker:
         if n_pos == 0 or len(subject_ids) == 0:
             z = np.empty((len(subject_ids), 0))
             return subject_ids, z.astype(np.int32), z.astype(np.float32), np.zeros(len(subject_ids), np.int32)
+        if getattr(self, "_subjects", None) is not None and getattr(self.engine, "subjects_owner", self) is not self:
+            # another ranker sharing this (cached) engine made its own subject factors resident in the meantime
+            self.engine.set_subjects(self._subjects, key=self._subjects_key, owner=self)
         ids, scores, counts = self.engine.topk(
             k, subject_ids=subject_ids, indptr=indptr, indices=indices, whitelist=whitelist, flags=flags
         )

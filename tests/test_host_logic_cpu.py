@@ -1,0 +1,93 @@
+"""CPU: host logic of `B200Ranker` / `B200ImplicitRanker` around the C ABI, with the shared library replaced by a recording
+stand-in (no compute): argument validation in the reference's terms, which calls reach the library, and when the resident
+subject factors are (re-)uploaded for rankers that share one cached engine."""
+import ctypes as C
+import types
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+
+class RecordingLib:
+    def __init__(self):
+        self.calls = []
+
+    def b200_rank_create(self, out, ptr, n, d, dist, device, tc, flags):
+        out._obj.value = 1 + len([c for c in self.calls if c[0] == "create"])  # pylint: disable=protected-access
+        self.calls.append(("create", int(n), int(d), int(dist)))
+        return 0
+
+    def b200_rank_destroy(self, h):
+        self.calls.append(("destroy", h.value))
+        return 0
+
+    def b200_rank_set_subjects(self, h, ptr, n, on_device):
+        self.calls.append(("set_subjects", h.value, int(n)))
+        return 0
+
+    def b200_rank_set_id_offset(self, h, off):
+        return 0
+
+    def b200_rank_topk(self, h, q, stats):
+        query = q._obj  # pylint: disable=protected-access
+        self.calls.append(("topk", h.value, int(query.n_rows), int(query.k), bool(query.csr_indptr), bool(query.whitelist)))
+        n, k = int(query.n_rows), int(query.k)
+        C.memset(query.out_counts, 0, 4 * n)  # every row: no results
+        return 0
+
+    def b200_rank_last_error(self):
+        return b""
+
+
+@pytest.fixture()
+def lib(monkeypatch):
+    from rectools_b200 import _lib, integration
+
+    rec = RecordingLib()
+    monkeypatch.setattr(_lib, "_LIB", rec)
+    integration.clear_engine_cache()
+    yield rec
+    integration._ENGINE_CACHE.clear()  # pylint: disable=protected-access
+
+
+def test_reference_error_contract(lib):
+    from rectools_b200 import B200Ranker
+
+    u, i = np.ones((5, 3), np.float32), np.ones((7, 3), np.float32)
+    ranker = B200Ranker("dot", u, i)
+    with pytest.raises(ValueError, match="filter_pairs_csr"):  # rank_implicit.py:215-217
+        ranker.rank([0, 1], k=2, filter_pairs_csr=sparse.csr_matrix((3, 7), dtype=np.float32))
+    with pytest.raises(ValueError):  # rank_implicit.py:66-67
+        B200Ranker("cosine", sparse.csr_matrix(u), i)
+    with pytest.raises(ValueError):
+        B200Ranker("dot", np.ones((5, 4), np.float32), i)
+    with pytest.raises(IndexError):
+        ranker.rank([0, 9], k=2)
+    s, ids, sc = ranker.rank([], k=3)
+    assert len(s) == len(ids) == len(sc) == 0 and not [c for c in lib.calls if c[0] == "topk"]
+    s, ids, sc = ranker.rank([1, 0], k=None, sorted_object_whitelist=np.array([2, 5]))  # k=None -> all (whitelisted) objects
+    assert [c for c in lib.calls if c[0] == "topk"][-1][2:] == (2, 2, False, True)
+    assert len(ids) == 0  # the stand-in returns no rows; counts = 0 must flatten to nothing
+
+
+def test_shared_cached_engine_keeps_the_right_subjects_resident(lib):
+    from rectools_b200 import B200ImplicitRanker
+
+    items = np.random.default_rng(0).random((50, 4), dtype=np.float32)
+    users_a = np.random.default_rng(1).random((20, 4), dtype=np.float32)
+    users_b = np.random.default_rng(2).random((30, 4), dtype=np.float32)
+    r1 = B200ImplicitRanker("dot", users_a, items)
+    r2 = B200ImplicitRanker("dot", users_a, items)  # same matrices: engine reused, subjects stay resident
+    assert [c[0] for c in lib.calls] == ["create", "set_subjects"]
+    r3 = B200ImplicitRanker("dot", users_b, items)  # same items, other subjects: one upload
+    assert [c[0] for c in lib.calls] == ["create", "set_subjects", "set_subjects"] and lib.calls[-1][2] == 30
+    r3.rank([0, 1], k=2)
+    assert [c[0] for c in lib.calls][-1] == "topk"
+    r1.rank([0, 1], k=2)  # r1's subjects were displaced by r3: uploaded again before ranking
+    assert [c[0] for c in lib.calls][-2:] == ["set_subjects", "topk"] and lib.calls[-2][2] == 20
+    r2.rank([0], k=1)  # same matrix as r1: nothing to upload
+    assert [c[0] for c in lib.calls][-2:] == ["topk", "topk"]
+    # COSINE needs its own engine (pre-normalised object copy)
+    B200ImplicitRanker("cosine", users_a, items)
+    assert [c for c in lib.calls if c[0] == "create"][-1][3] == 1 and len([c for c in lib.calls if c[0] == "create"]) == 2
