@@ -59,7 +59,9 @@ def _rows_of(csr: tp.Any, user_ids: np.ndarray) -> tp.Any:
     n = csr.shape[0]
     if len(user_ids) == n and (n == 0 or (user_ids[0] == 0 and user_ids[-1] == n - 1 and (np.diff(user_ids) == 1).all())):
         return csr
-    return csr[user_ids]
+    rows = csr[user_ids]
+    rows.has_sorted_indices = True  # row selection keeps the (sorted) order inside every row: spare the ranker an O(nnz) check
+    return rows
 
 
 def finalize_scores(ranker: tp.Any, subject_ids: np.ndarray, scores: np.ndarray) -> np.ndarray:
