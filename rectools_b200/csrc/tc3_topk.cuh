@@ -103,8 +103,8 @@ __device__ __forceinline__ uint32_t pin(uint32_t x) {
 }
 
 // Maximum of the 32 staged scores r[OFF .. OFF+32) (11 three-input maxima + 1).
-template <int OFF>
-__device__ __forceinline__ float chunk_max(const uint32_t (&r)[T3_HALF]) {
+template <int OFF, int NR>
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[NR]) {
     const float g0 = max3(max3(fu(r[OFF + 0]), fu(r[OFF + 1]), fu(r[OFF + 2])), max3(fu(r[OFF + 3]), fu(r[OFF + 4]), fu(r[OFF + 5])),
                           max3(fu(r[OFF + 6]), fu(r[OFF + 7]), fu(r[OFF + 8])));
     const float g1 = max3(max3(fu(r[OFF + 9]), fu(r[OFF + 10]), fu(r[OFF + 11])), max3(fu(r[OFF + 12]), fu(r[OFF + 13]), fu(r[OFF + 14])),
@@ -115,8 +115,8 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[T3_HALF]) {
     return fmaxf(max3(g0, g1, g2), g3);
 }
 
-template <int OFF, int J0, int J1>
-__device__ __forceinline__ unsigned group_mask(const uint32_t (&r)[T3_HALF], float thr) {
+template <int OFF, int J0, int J1, int NR>
+__device__ __forceinline__ unsigned group_mask(const uint32_t (&r)[NR], float thr) {
     unsigned m = 0;
 #pragma unroll
     for (int j = J0; j < J1; ++j) m |= (fu(r[OFF + j]) > thr) ? (1u << j) : 0u;
@@ -125,8 +125,8 @@ __device__ __forceinline__ unsigned group_mask(const uint32_t (&r)[T3_HALF], flo
 
 // Per-lane bit mask of the columns of chunk OFF above the row threshold; the mask of a 9-column group is built only
 // when the group's maximum shows a hit somewhere in the warp.
-template <int OFF>
-__device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[T3_HALF], float thr) {
+template <int OFF, int NR>
+__device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[NR], float thr) {
     const float g0 = max3(max3(fu(r[OFF + 0]), fu(r[OFF + 1]), fu(r[OFF + 2])), max3(fu(r[OFF + 3]), fu(r[OFF + 4]), fu(r[OFF + 5])),
                           max3(fu(r[OFF + 6]), fu(r[OFF + 7]), fu(r[OFF + 8])));
     const float g1 = max3(max3(fu(r[OFF + 9]), fu(r[OFF + 10]), fu(r[OFF + 11])), max3(fu(r[OFF + 12]), fu(r[OFF + 13]), fu(r[OFF + 14])),
@@ -143,8 +143,8 @@ __device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[T3_HALF], flo
 }
 
 // r[OFF + j] for a run-time j without local memory: 5-level select tree (31 SEL).
-template <int OFF>
-__device__ __forceinline__ float chunk_select(const uint32_t (&r)[T3_HALF], int j) {
+template <int OFF, int NR>
+__device__ __forceinline__ float chunk_select(const uint32_t (&r)[NR], int j) {
     uint32_t a[16], b[8], c[4], d[2];
     const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
 #pragma unroll
@@ -177,11 +177,11 @@ __device__ __forceinline__ void window_load(const int32_t* __restrict__ indices,
 
 // Move this thread's pending hits of chunk OFF (ascending column order) into its FIFO (a ring of T3_Q slots).  Returns
 // true when some lane still has hits but no free slot: the caller runs a fifo_step and calls again with the remaining mask.
-template <int OFF>
-__device__ __forceinline__ bool chunk_push(const uint32_t (&r)[T3_HALF], unsigned& hits, uint32_t pos0, float thr, uint32_t n_pos,
+template <int OFF, int QN = T3_Q, int QS = T3_QSTRIDE, int NR>
+__device__ __forceinline__ bool chunk_push(const uint32_t (&r)[NR], unsigned& hits, uint32_t pos0, float thr, uint32_t n_pos,
                                            uint32_t qaddr, int head, int& tail) {
     while (__any_sync(B200_FULL_MASK, hits != 0)) {
-        if (hits && tail - head < T3_Q) {
+        if (hits && tail - head < QN) {
             const int j = __ffs(hits) - 1;
             hits &= hits - 1;
             // (taking the chunk maximum when it is the only score above the threshold, instead of the select tree, measured
@@ -189,11 +189,11 @@ __device__ __forceinline__ bool chunk_push(const uint32_t (&r)[T3_HALF], unsigne
             const float val = chunk_select<OFF>(r, j);
             const uint32_t pos = pos0 + (uint32_t)(OFF + j);
             if (val > thr && pos < n_pos) {
-                sts_v2(qaddr + (uint32_t)(tail & (T3_Q - 1)) * T3_QSTRIDE, val, pos);
+                sts_v2(qaddr + (uint32_t)(tail & (QN - 1)) * QS, val, pos);
                 ++tail;
             }
         }
-        if (__any_sync(B200_FULL_MASK, hits != 0 && tail - head == T3_Q)) return true;
+        if (__any_sync(B200_FULL_MASK, hits != 0 && tail - head == QN)) return true;
     }
     return false;
 }
@@ -202,12 +202,13 @@ __device__ __forceinline__ bool chunk_push(const uint32_t (&r)[T3_HALF], unsigne
 // look at the oldest pending hit of the row; drop it if the threshold has passed it; if it lies beyond the CSR window,
 // move the window (loads issued, not waited for) and leave the hit for the next step; otherwise test it against the
 // window / the exclusion list and insert it into the row's candidate list.
+template <int QN = T3_Q, int QS = T3_QSTRIDE>
 __device__ __forceinline__ void fifo_step(const TcParams& p, RowState& rs, CsrWindow& cw, uint32_t qaddr, int& head, int tail,
                                           uint32_t ls, uint32_t li, int kc) {
     if (head == tail) return;
     float val;
     uint32_t pos;
-    lds_v2(qaddr + (uint32_t)(head & (T3_Q - 1)) * T3_QSTRIDE, val, pos);
+    lds_v2(qaddr + (uint32_t)(head & (QN - 1)) * QS, val, pos);
     if (!(val > rs.thr)) {
         ++head;
         return;
