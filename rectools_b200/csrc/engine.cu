@@ -24,6 +24,7 @@
 #include "tc_topk.cuh"
 #include "tc2_topk.cuh"
 #include "tc3_topk.cuh"
+#include "tc4_topk.cuh"
 
 namespace {
 
@@ -134,6 +135,7 @@ struct b200_rank_engine {
     const float* obj32_ptr = nullptr;
     CUtensorMap tm_obj_full;
     bool tm_obj_ok = false;
+    bool tc4_ok = false;  // experimental tc4_topk_kernel usable (B200_TC_KERNEL=4)
 
     // resident subjects (optional)
     DevBuf sub32_res;
@@ -282,6 +284,22 @@ TcPlan plan_tc3(int d_pad) {
     return pl;
 }
 
+// Shared-memory plan of the experimental 16-epilogue-warp kernel (tc4_topk.cuh).
+TcPlan plan_tc4(int d_pad) {
+    TcPlan pl{};
+    pl.kblocks = d_pad / tc::KBLK;
+    pl.s_sub = 2;
+    const int a = pl.kblocks * tc::BLK_BYTES;
+    const int lists = 2 * tc::T4_LIST_BYTES + 4 * tc::TILE_M * 8 + tc::T4_QBYTES;
+    const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
+    int stages = (tc::SMEM_LIMIT - fixed) / tc::BLK_BYTES;
+    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+    pl.ok = stages >= 2;
+    pl.n_stages = stages;
+    pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
+    return pl;
+}
+
 uint32_t make_idesc2(bool bf16, int tile_n) {
     uint32_t d = 0;
     d |= 1u << 4;
@@ -369,6 +387,13 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
             }
             TcPlan pl2 = plan_tc2(E->d_pad, 256), pl2b = plan_tc2(E->d_pad, 128), pl3 = plan_tc3(E->d_pad);
             if (pl3.ok) CK(cudaFuncSetAttribute(tc::tc3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl3.smem_bytes));
+            TcPlan pl4 = plan_tc4(E->d_pad);  // experimental kernel: never allowed to fail the engine
+            if (pl4.ok) {
+                if (cudaFuncSetAttribute(tc::tc4_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl4.smem_bytes) == cudaSuccess)
+                    E->tc4_ok = true;
+                else
+                    (void)cudaGetLastError();
+            }
             if (pl2.ok) {
                 CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
                 CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
@@ -589,7 +614,8 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         // ---------------- path choice
         TcPlan pl = plan_tc(E->d_pad);
         // 2-SM kernel (CTA pairs, cta_group::2) unless disabled or impossible; B200_TC_KERNEL=1 selects the 1-SM kernel
-        // B200_TC_KERNEL: 1 = 1-SM kernel (tc_topk.cuh), 2 = previous 2-SM kernel (tc2_topk.cuh), default 3 = tc3_topk.cuh
+        // B200_TC_KERNEL: 1 = 1-SM kernel (tc_topk.cuh), 2 = previous 2-SM kernel (tc2_topk.cuh), default 3 = tc3_topk.cuh,
+        // 4 = experimental tc4_topk.cuh for passes with K' <= 16 (everything else of such a call runs on tc3)
         bool use_2sm = (E->sm_count % 2 == 0);
         int kernel_gen = 3;
         if (const char* env = getenv("B200_TC_KERNEL")) {
@@ -607,6 +633,8 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             else
                 use_gen3 = false;
         }
+        const TcPlan pl4 = plan_tc4(E->d_pad);
+        const bool use_gen4 = use_gen3 && kernel_gen == 4 && pl4.ok && E->tc4_ok;
         if (use_2sm && !use_gen3) {
             TcPlan pl2 = plan_tc2(E->d_pad, tile2_n);
             if (pl2.ok)
@@ -620,7 +648,11 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         // certificate and take the second-chance pass.  Inserts, the dominant epilogue cost, scale with K'.
         int k_cand = 0;
         const bool bf16_tc = E->tc_dtype == B200_TC_BF16;
-        if (use_2sm) {
+        if (use_gen4 && k_out <= 24) {
+            // four lists per row: a list may be SHORTER than k (the certificate only needs the k-th exact score above every
+            // full list's minimum); rows whose top-k crowd into one column quarter take the second-chance pass
+            k_cand = std::min(tc::T4_SLOTS, (k_out <= 10 ? 8 : k_out <= 16 ? 12 : 16) + (bf16_tc ? 2 : 0));
+        } else if (use_2sm) {
             const int surplus = bf16_tc ? std::max(6, k_out / 2) : std::max(2, k_out / 4);
             if (k_out <= 24) k_cand = std::min(32, k_out + surplus);
             else if (k_out <= 128) k_cand = 25;  // multi-pass, see below
@@ -632,7 +664,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         }
         if (const char* env = getenv("B200_TC_KCAND")) {  // tuning hook
             const int forced = atoi(env);
-            if (forced >= k_out && forced <= 32) k_cand = forced;
+            if ((forced >= k_out || use_gen4) && forced >= 4 && forced <= 32) k_cand = forced;
         }
         bool use_tc = E->tc_dtype != B200_TC_OFF && pl.ok && k_cand > 0 && !(q->flags & B200_Q_FORCE_EXACT) &&
                       n_pos >= (int64_t)k_cand * 4;
@@ -723,7 +755,9 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int k0, int kp, int32_t* fb_list, int32_t* fb_count,
                               bool timed) -> int64_t {
                 const bool bf16 = E->tc_dtype == B200_TC_BF16;
-                const int rows_per_cta = pl.s_sub * tc::TILE_M;
+                const bool g4 = use_gen4 && kc <= tc::T4_SLOTS;  // this pass on the experimental kernel
+                const TcPlan& plx = g4 ? pl4 : pl;
+                const int rows_per_cta = plx.s_sub * tc::TILE_M;
                 const int64_t rows_pad = round_up(n_sel, rows_per_cta);
                 // subjects -> 16-bit, per-row power-of-two scale
                 E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
@@ -764,15 +798,15 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                     throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled", __LINE__};
 
                 tc::TcParams tp{};
-                tp.s_sub = pl.s_sub;
-                tp.kblocks = pl.kblocks;
-                tp.n_stages = pl.n_stages;
+                tp.s_sub = plx.s_sub;
+                tp.kblocks = plx.kblocks;
+                tp.n_stages = plx.n_stages;
                 tp.k_cand = kc;
                 tp.n_rows = n_sel;
                 tp.n_pos = n_pos;
                 tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
                 const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
-                const int lists_per_split = use_2sm ? 2 : 1;
+                const int lists_per_split = g4 ? 4 : use_2sm ? 2 : 1;
                 tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
                 // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
                 int best_splits = 1;
@@ -837,7 +871,9 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                     const int grid = 2 * std::min(n_work, n_units);
                     bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
                     if (const char* env = getenv("B200_TC_STAGE")) stage_regs = atoi(env) != 0;
-                    if (use_gen3)
+                    if (g4)
+                        tc::tc4_topk_kernel<<<grid, tc::T4_THREADS, plx.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+                    else if (use_gen3)
                         tc::tc3_topk_kernel<<<grid, tc::T3_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
                     else if (tile2_n == 256 && stage_regs)
                         tc::tc2_topk_kernel<256, 2, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
