@@ -1,9 +1,8 @@
-bench p4b2 ""
-bench p2b2 "" B200_RANK_LIB=$L/libb200rank_p2.so
-bench p8b2 "" B200_RANK_LIB=$L/libb200rank_p8.so
-bench p8b3 "" B200_RANK_LIB=$L/libb200rank_p8b3.so
-bench p16q8b4 "" B200_RANK_LIB=$L/libb200rank_p16q8b4.so
-bench p4b2_n125k "--items 125000"
-bench p8b2_n125k "--items 125000" B200_RANK_LIB=$L/libb200rank_p8.so
-bench p8b3_n125k "--items 125000" B200_RANK_LIB=$L/libb200rank_p8b3.so
-bench p16q8b4_n125k "--items 125000" B200_RANK_LIB=$L/libb200rank_p16q8b4.so
+# round-2 starting point: the experimental 16-epilogue-warp kernel against the default
+bench gen3 ""
+bench gen4 "" B200_TC_KERNEL=4
+bench gen4_kc10 "" B200_TC_KERNEL=4 B200_TC_KCAND=10
+bench gen4_kc6 "" B200_TC_KERNEL=4 B200_TC_KCAND=6
+bench gen3_n125k "--items 125000"
+bench gen4_n125k "--items 125000" B200_TC_KERNEL=4
+bench gen4_1M "--users 1000000" B200_TC_KERNEL=4

@@ -215,8 +215,11 @@ def test_multi_pass_tensor_core_large_k(rb, distance, k, use_wl):
         {"B200_TC_KERNEL": "2", "B200_TC_TILE": "128"},
         {"B200_TC_KERNEL": "2", "B200_TC_TILE": "128", "B200_TC_STAGE": "0"},
         {"B200_TC_KERNEL": "1"},
+        # experimental kernel, not validated on hardware yet: B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k gen4
+        pytest.param({"B200_TC_KERNEL": "4"}, marks=pytest.mark.skipif(not os.environ.get("B200_TEST_EXPERIMENTAL"),
+                                                                         reason="tc4_topk.cuh is experimental")),
     ],
-    ids=["gen3", "2sm256stage", "2sm256", "2sm128stage", "2sm128", "1sm"],
+    ids=["gen3", "2sm256stage", "2sm256", "2sm128stage", "2sm128", "1sm", "gen4"],
 )
 def test_many_work_items_per_cta(rb, monkeypatch, splits, kernel_env):
     """More subject tiles than CTAs (persistent loop, accumulator / list / threshold hand-over between work items) and
