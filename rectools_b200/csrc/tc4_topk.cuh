@@ -183,7 +183,7 @@ tc4_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constan
         const uint32_t li = pin(smem_u32(sLi) + (uint32_t)((colq * TILE_M + wrow0) * T4_SLOTS * 4) + lane * 4);
         const uint32_t qaddr = pin(smem_u32(sQ) + (uint32_t)(ew * 32 + lane) * 8);
         const uint32_t thr_row = pin(smem_u32(sThr + wrow0 + lane));  // + colq * 128 * 8: the four threads of this row
-        const uint32_t my_thr = thr_row + (uint32_t)colq * (TILE_M * 8);
+        const uint32_t my_thr = pin(thr_row + (uint32_t)colq * (TILE_M * 8));
         const uint32_t tempty0 = pin(mapa_rank(bar_tempty, 0)), tempty1 = pin(mapa_rank(bar_tempty + 8, 0));  // the leader's copies
         const uint32_t tfull0 = pin(bar_tfull), tfull1 = pin(bar_tfull + 8);
         const uint32_t tbase = pin(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colq * T4_COLS));
