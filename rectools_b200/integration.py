@@ -11,7 +11,6 @@ Seams:
 from __future__ import annotations
 
 import typing as tp
-import weakref
 
 import numpy as np
 
@@ -174,5 +173,3 @@ def make_similarity_module() -> type:
 
     return B200DistanceSimilarityModule
 
-
-del weakref
