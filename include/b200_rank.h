@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define B200_RANK_ABI_VERSION 2
+#define B200_RANK_ABI_VERSION 3
 
 /* error codes */
 #define B200_OK 0
@@ -76,6 +76,14 @@ extern "C" {
 #define B200_Q_OUTPUTS_ON_DEVICE 2 /* out_* are device pointers */
 #define B200_Q_FORCE_EXACT 4       /* skip the tensor-core pass */
 #define B200_Q_FORCE_TC 8          /* fail with B200_E_UNSUPPORTED instead of silently using the exhaustive kernel */
+#define B200_Q_SHARED_THRESHOLDS 16 /* item-sharded multi-GPU pass: prune with the maximum of all ranks' thresholds (peer memory
+                                     * set up by b200_rank_peer_*), no local verdict: `out_bounds` must be given and the global
+                                     * top-k is certified by b200_rank_merge_certified.  Needs k <= 24. */
+
+/* element types of factor matrices handed over as device pointers (b200_rank_create_ex / query.subject_dtype) */
+#define B200_DT_F32 0
+#define B200_DT_F16 1
+#define B200_DT_BF16 2
 
 typedef struct b200_rank_engine b200_rank_engine;
 
@@ -103,6 +111,19 @@ typedef struct b200_rank_query {
     void* stream;        /* cudaStream_t the device buffers are produced / consumed on; the call is ordered after the work
                           * queued on it and it waits for the results.  NULL = the (legacy) default stream.  Ignored when
                           * every buffer is a host buffer. */
+    /* ---- ABI 3 */
+    float* out_bounds;   /* B200_Q_SHARED_THRESHOLDS: [n_rows] upper bound on the exact score of every object of this shard that
+                          * is NOT among the row's returned candidates (-inf: nothing was discarded); same memory space as out_* */
+    uint32_t peer_epoch; /* B200_Q_SHARED_THRESHOLDS: tag of this call, >= 1, the same on every rank, different from the
+                          * previous call's */
+    int32_t subject_dtype; /* B200_DT_* of `subjects` (device pointers only; host matrices are fp32) */
+    /* sparse subjects (EASEModel: subjects_factors is the user x item CSR, rectools/models/ease.py:134-161, DOT only):
+     * row r of the batch = sub_indices / sub_data [sub_indptr[r], sub_indptr[r+1]); columns index the d factor columns.
+     * Given instead of `subjects` / `subject_ids`. */
+    const int64_t* sub_indptr; /* [n_rows + 1] or NULL */
+    const int32_t* sub_indices;
+    const float* sub_data;
+    int64_t reserved[2];
 } b200_rank_query;
 
 typedef struct b200_rank_stats {
@@ -121,6 +142,10 @@ typedef struct b200_rank_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     int32_t n_chunks;        /* row chunks of the copy / compute pipeline (1: call not chunked) */
+    int32_t n_tc_launches;   /* launches of the fused tensor-core kernel summed in ms_main (main pass, second chance, re-rank passes) */
+    int32_t epi_warps;       /* epilogue warps per CTA of the fused kernel (8 or 16) */
+    int32_t wide;            /* 1: single-pass wide mode (24 < k <= 128) */
+    float ms_select;         /* CUDA-event time of the fp64 re-score / selection kernels */
     int32_t reserved;
 } b200_rank_stats;
 
@@ -140,6 +165,11 @@ typedef struct b200_rank_info {
 
 int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_objects, int32_t d, int32_t distance,
                      int32_t device, int32_t tc_mode, int32_t flags);
+/* The same with an explicit element type: fp16 / bf16 object factors (transformer id-embedding scorers keep `item_embs`
+ * in the model dtype, rectools/models/nn/transformers/lightning.py:391-398).  16-bit matrices must be device pointers
+ * (B200_F_OBJECTS_ON_DEVICE); they are widened once into the engine's fp32 master copy, which is exact. */
+int b200_rank_create_ex(b200_rank_engine** out, const void* objects, int32_t dtype, int64_t n_objects, int32_t d,
+                        int32_t distance, int32_t device, int32_t tc_mode, int32_t flags);
 int b200_rank_destroy(b200_rank_engine* engine);
 int b200_rank_set_subjects(b200_rank_engine* engine, const float* subjects, int64_t n_subjects, int32_t on_device);
 /* Item-sharded catalogues: the engine holds objects [offset, offset + n_objects) of a larger catalogue.  CSR column ids
@@ -153,6 +183,24 @@ int b200_rank_get_info(b200_rank_engine* engine, b200_rank_info* info);
 int b200_rank_merge(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids,
                     const float* scores, const int32_t* counts, int32_t* out_ids, float* out_scores,
                     int32_t* out_counts);
+
+/* The same over per-shard results that carry certificate bounds (B200_Q_SHARED_THRESHOLDS passes): list l's arrays start
+ * `list_stride` ELEMENTS (4-byte units) after list l-1's (one packed buffer per rank after an all-gather; 0 = dense arrays
+ * as in b200_rank_merge).  Rows whose k-th merged score does not exceed every shard's bound are appended to `fail_rows`
+ * (device, [n_rows]) and counted in `fail_count` (device int32, zeroed by the caller): they must be re-ranked without
+ * threshold sharing. */
+int b200_rank_merge_certified(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids,
+                              const float* scores, const int32_t* counts, const float* bounds, int64_t list_stride,
+                              int32_t* out_ids, float* out_scores, int32_t* out_counts, int32_t* fail_rows,
+                              int32_t* fail_count);
+
+/* Threshold sharing between the ranks of an item-sharded catalogue (one process per GPU, NVLink peer memory):
+ *   export: allocate this engine's published-threshold array for calls of up to `max_rows` subject rows and return its
+ *           64-byte CUDA IPC handle;
+ *   import: open the arrays of all `n_ranks` ranks (`handles` = n_ranks x 64 bytes, in rank order; entry `self` is this
+ *           engine's own and is skipped).  At most 9 ranks. */
+int b200_rank_peer_export(b200_rank_engine* engine, int64_t max_rows, void* handle_out);
+int b200_rank_peer_import(b200_rank_engine* engine, int32_t n_ranks, int32_t self, const void* handles);
 
 const char* b200_rank_last_error(void);
 int b200_rank_abi_version(void);

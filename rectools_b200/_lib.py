@@ -10,21 +10,26 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200_RANK_LIB") or os.path.join(HERE, "libb200rank.so")
 
 # mirrors of the #defines in include/b200_rank.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 DIST_DOT, DIST_COSINE = 0, 1
 TC_AUTO, TC_FP16, TC_BF16, TC_OFF = 0, 1, 2, 3
 F_OBJECTS_ON_DEVICE = 1
-Q_INPUTS_ON_DEVICE, Q_OUTPUTS_ON_DEVICE, Q_FORCE_EXACT, Q_FORCE_TC = 1, 2, 4, 8
+Q_INPUTS_ON_DEVICE, Q_OUTPUTS_ON_DEVICE, Q_FORCE_EXACT, Q_FORCE_TC, Q_SHARED_THRESHOLDS = 1, 2, 4, 8, 16
+DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 
 EXPORTS = (
     "b200_rank_create",
+    "b200_rank_create_ex",
     "b200_rank_destroy",
     "b200_rank_set_subjects",
     "b200_rank_set_id_offset",
     "b200_rank_topk",
     "b200_rank_get_info",
     "b200_rank_merge",
+    "b200_rank_merge_certified",
+    "b200_rank_peer_export",
+    "b200_rank_peer_import",
     "b200_rank_last_error",
     "b200_rank_abi_version",
 )
@@ -46,6 +51,13 @@ class Query(C.Structure):
         ("out_scores", C.c_void_p),
         ("out_counts", C.c_void_p),
         ("stream", C.c_void_p),
+        ("out_bounds", C.c_void_p),
+        ("peer_epoch", C.c_uint32),
+        ("subject_dtype", C.c_int32),
+        ("sub_indptr", C.c_void_p),
+        ("sub_indices", C.c_void_p),
+        ("sub_data", C.c_void_p),
+        ("reserved", C.c_int64 * 2),
     ]
 
 
@@ -66,11 +78,15 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
         ("n_chunks", C.c_int32),
+        ("n_tc_launches", C.c_int32),
+        ("epi_warps", C.c_int32),
+        ("wide", C.c_int32),
+        ("ms_select", C.c_float),
         ("reserved", C.c_int32),
     ]
 
     def as_dict(self) -> tp.Dict[str, tp.Any]:
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
 
 
 class Info(C.Structure):
@@ -110,6 +126,8 @@ def load() -> C.CDLL:
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.b200_rank_create.restype = C.c_int
     lib.b200_rank_create.argtypes = [C.POINTER(vp), vp, i64, i32, i32, i32, i32, i32]
+    lib.b200_rank_create_ex.restype = C.c_int
+    lib.b200_rank_create_ex.argtypes = [C.POINTER(vp), vp, i32, i64, i32, i32, i32, i32, i32]
     lib.b200_rank_destroy.restype = C.c_int
     lib.b200_rank_destroy.argtypes = [vp]
     lib.b200_rank_set_subjects.restype = C.c_int
@@ -122,6 +140,12 @@ def load() -> C.CDLL:
     lib.b200_rank_get_info.argtypes = [vp, C.POINTER(Info)]
     lib.b200_rank_merge.restype = C.c_int
     lib.b200_rank_merge.argtypes = [i32, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp]
+    lib.b200_rank_merge_certified.restype = C.c_int
+    lib.b200_rank_merge_certified.argtypes = [i32, vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.b200_rank_peer_export.restype = C.c_int
+    lib.b200_rank_peer_export.argtypes = [vp, i64, vp]
+    lib.b200_rank_peer_import.restype = C.c_int
+    lib.b200_rank_peer_import.argtypes = [vp, i32, i32, vp]
     lib.b200_rank_last_error.restype = C.c_char_p
     lib.b200_rank_last_error.argtypes = []
     lib.b200_rank_abi_version.restype = C.c_int

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rank.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "prep.cuh", "select.cuh", "tc_topk.cuh", "tc2_topk.cuh", "tc3_topk.cuh", "tc4_topk.cuh", os.path.join("..", "..", "include", "b200_rank.h")]
+HEADERS = ["common.cuh", "prep.cuh", "select.cuh", "sparse.cuh", "tc_common.cuh", "fused_topk.cuh", os.path.join("..", "..", "include", "b200_rank.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

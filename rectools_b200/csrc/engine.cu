@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -21,10 +22,8 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "select.cuh"
-#include "tc_topk.cuh"
-#include "tc2_topk.cuh"
-#include "tc3_topk.cuh"
-#include "tc4_topk.cuh"
+#include "sparse.cuh"
+#include "fused_topk.cuh"
 
 namespace {
 
@@ -91,12 +90,12 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 // Row-major [rows, d_pad] 16-bit matrix, boxes of [128 rows x 64 cols] (128-byte rows, SWIZZLE_128B).
-bool make_tensor_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, bool is_bf16, int box_rows = 128) {
+bool make_tensor_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad, bool is_bf16) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)b200::tc::KBLK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)b200::tc::KBLK, 128u};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -105,6 +104,11 @@ bool make_tensor_map(CUtensorMap* tm, const void* base, int64_t rows, int d_pad,
 }
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 
 }  // namespace
 
@@ -123,52 +127,62 @@ struct b200_rank_engine {
     cudaStream_t cs = nullptr;          // copy stream of the chunk pipeline
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t evp[3] = {nullptr};     // chunk pipeline: inputs of chunk c / c+1 staged, stream hand-over
+    std::vector<cudaEvent_t> evt;       // timing pairs of the fused-kernel / selection launches of a call
 
     // resident object data
     DevBuf obj32;     // [n_obj, d] fp32 master copy
     DevBuf obj16;     // [n_obj_pad, d_pad] fp16 / bf16, pre-scaled (and pre-normalised for COSINE)
     DevBuf obj_norms; // [n_obj] fp32 (COSINE)
+    DevBuf objT;      // [d, n_obj] fp32 transposed master copy (sparse subjects only, built on first use)
     int obj_exp = 0;
     int64_t id_offset = 0;
     float max_obj_norm = 0.f;
-    bool obj32_owned = true;
     const float* obj32_ptr = nullptr;
-    CUtensorMap tm_obj_full;
-    bool tm_obj_ok = false;
-    bool tc4_ok = false;  // experimental tc4_topk_kernel usable (B200_TC_KERNEL=4)
 
     // resident subjects (optional)
     DevBuf sub32_res;
     int64_t n_sub_res = 0;
     const float* sub32_res_ptr = nullptr;
 
+    // threshold sharing with the other ranks of an item-sharded catalogue
+    DevBuf peer_pub;
+    int64_t peer_rows = 0;
+    int n_peers = 0;
+    void* peer_in[b200::tc::MAX_PEERS] = {nullptr};
+
     // per-call staging / workspace
     DevBuf sub32, sub16, row_exp, rowmap, indptr, indices, wl, obj16_wl;
-    DevBuf out_ids, out_scores, out_counts;
-    DevBuf cand_scores, cand_ids, cand_counts;
+    DevBuf sp_indptr, sp_indices, sp_data, sp_scores;
+    DevBuf out_ids, out_scores, out_counts, out_bounds;
+    DevBuf cand_scores, cand_ids, cand_counts, cand_thr;
     DevBuf part_scores, part_ids;
-    DevBuf fb_rows, scratch, excl, carousel;
-    int32_t* h_pinned = nullptr;  // small pinned scratch (fallback count)
+    DevBuf fb_rows, scratch, excl, carousel, patch;
+    int32_t* h_pinned = nullptr;  // small pinned scratch (counters)
+    std::vector<char> h_patch;    // host copy of re-ranked rows (host-output calls)
 
-    size_t hbm_bytes() const {
-        const DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
-                               &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
-                               &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl, &carousel};
+    std::vector<DevBuf*> all_bufs() {
+        return {&obj32, &obj16, &obj_norms, &objT, &sub32_res, &peer_pub, &sub32, &sub16, &row_exp, &rowmap, &indptr, &indices, &wl,
+                &obj16_wl, &sp_indptr, &sp_indices, &sp_data, &sp_scores, &out_ids, &out_scores, &out_counts, &out_bounds, &cand_scores,
+                &cand_ids, &cand_counts, &cand_thr, &part_scores, &part_ids, &fb_rows, &scratch, &excl, &carousel, &patch};
+    }
+    size_t hbm_bytes() {
         size_t t = 0;
-        for (auto* b : all) t += b->cap;
+        for (auto* b : all_bufs()) t += b->cap;
         return t;
     }
     void free_all() {
-        DevBuf* all[] = {&obj32, &obj16, &obj_norms, &sub32_res, &sub32, &sub16, &row_exp, &rowmap, &indptr,
-                         &indices, &wl, &obj16_wl, &out_ids, &out_scores, &out_counts, &cand_scores, &cand_ids,
-                         &cand_counts, &part_scores, &part_ids, &fb_rows, &scratch, &excl, &carousel};
-        for (auto* b : all) b->release();
+        for (int i = 0; i < b200::tc::MAX_PEERS; ++i)
+            if (peer_in[i]) cudaIpcCloseMemHandle(peer_in[i]);
+        for (auto* b : all_bufs()) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         for (auto& e : evp)
             if (e) cudaEventDestroy(e);
+        for (auto& e : evt)
+            if (e) cudaEventDestroy(e);
+        evt.clear();
         if (st) cudaStreamDestroy(st);
         if (cs) cudaStreamDestroy(cs);
         st = cs = nullptr;
@@ -202,13 +216,13 @@ void prepare_objects(b200_rank_engine* E, int tc_mode) {
     memcpy(&maxnorm, &h[1], 4);
     E->max_obj_norm = maxnorm;
 
-    if (tc_mode == B200_TC_OFF || E->cc_major != 10) {
+    if (tc_mode == B200_TC_OFF || E->cc_major != 10 || E->sm_count % 2 != 0) {
         E->tc_dtype = B200_TC_OFF;
         return;
     }
     E->tc_dtype = (tc_mode == B200_TC_BF16) ? B200_TC_BF16 : B200_TC_FP16;
     E->obj_exp = (E->tc_dtype == B200_TC_FP16) ? fp16_scale_exp(absmax) : 0;
-    E->n_obj_pad = round_up(std::max<int64_t>(n, 1), tc::TILE_N);
+    E->n_obj_pad = round_up(std::max<int64_t>(n, 1), tc::HALF_N);
     E->obj16.ensure((size_t)E->n_obj_pad * E->d_pad * 2);
     const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
     const int grid = grid_for(E->n_obj_pad * 32, 256);
@@ -220,94 +234,25 @@ void prepare_objects(b200_rank_engine* E, int tc_mode) {
                                                                            norms, 0, 0, E->obj16.as<__nv_bfloat16>(), nullptr);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(E->st));
-    E->tm_obj_ok = make_tensor_map(&E->tm_obj_full, E->obj16.p, E->n_obj_pad, E->d_pad, E->tc_dtype == B200_TC_BF16);
-    if (!E->tm_obj_ok) E->tc_dtype = B200_TC_OFF;
 }
 
+// Shared-memory plan of the fused kernel: subject blocks + object ring + the fixed part of FusedCfg<NW>.
 struct TcPlan {
-    int s_sub, kblocks, n_stages, smem_bytes;
+    int kblocks, n_stages, smem_bytes;
     bool ok;
 };
 
-TcPlan plan_tc(int d_pad) {
+template <int NW>
+TcPlan plan_fused(int d_pad) {
     TcPlan pl{};
     pl.kblocks = d_pad / tc::KBLK;
-    for (int s = 2; s >= 1; --s) {
-        const int a = s * pl.kblocks * tc::BLK_BYTES;
-        const int lists = s * tc::TILE_M * 32 * 8;
-        const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
-        const int avail = tc::SMEM_LIMIT - fixed;
-        int stages = avail / tc::BLK_BYTES;
-        if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-        if (stages >= 3 || (s == 1 && stages >= 2)) {
-            pl.s_sub = s;
-            pl.n_stages = stages;
-            pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
-            pl.ok = true;
-            return pl;
-        }
-    }
-    pl.ok = false;
-    return pl;
-}
-
-// Shared-memory plan of the 2-SM kernel (per CTA: 128 subject rows, half of every object tile).
-TcPlan plan_tc2(int d_pad, int tile_n) {
-    TcPlan pl{};
-    pl.kblocks = d_pad / tc::KBLK;
-    pl.s_sub = 2;  // two candidate lists per row (one per column half)
-    const int a = pl.kblocks * tc::BLK_BYTES;
-    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8;
-    const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
-    const int blkb = tile_n / 2 * tc::KBLK * 2;  // object block bytes per CTA
-    int stages = (tc::SMEM_LIMIT - fixed) / blkb;
-    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-    pl.ok = stages >= 2;
-    pl.n_stages = stages;
-    pl.smem_bytes = fixed + stages * blkb;
-    return pl;
-}
-
-// Shared-memory plan of the default kernel (tc3_topk.cuh): as plan_tc2(d_pad, 256) plus the deferred-hit FIFOs.
-TcPlan plan_tc3(int d_pad) {
-    TcPlan pl{};
-    pl.kblocks = d_pad / tc::KBLK;
-    pl.s_sub = 2;
-    const int a = pl.kblocks * tc::BLK_BYTES;
-    const int lists = 2 * tc::TILE_M * 32 * 8 + 2 * tc::TILE_M * 8 + tc::T3_QBYTES;
-    const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
+    const int fixed = pl.kblocks * tc::BLK_BYTES + tc::FusedCfg<NW>::FIXED_BYTES;
     int stages = (tc::SMEM_LIMIT - fixed) / tc::BLK_BYTES;
     if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
     pl.ok = stages >= 2;
     pl.n_stages = stages;
     pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
     return pl;
-}
-
-// Shared-memory plan of the experimental 16-epilogue-warp kernel (tc4_topk.cuh).
-TcPlan plan_tc4(int d_pad) {
-    TcPlan pl{};
-    pl.kblocks = d_pad / tc::KBLK;
-    pl.s_sub = 2;
-    const int a = pl.kblocks * tc::BLK_BYTES;
-    const int lists = 2 * tc::T4_LIST_BYTES + 4 * tc::TILE_M * 8 + tc::T4_QBYTES;
-    const int fixed = a + lists + 1024 /*alignment slack*/ + 512 /*barriers*/;
-    int stages = (tc::SMEM_LIMIT - fixed) / tc::BLK_BYTES;
-    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-    pl.ok = stages >= 2;
-    pl.n_stages = stages;
-    pl.smem_bytes = fixed + stages * tc::BLK_BYTES;
-    return pl;
-}
-
-uint32_t make_idesc2(bool bf16, int tile_n) {
-    uint32_t d = 0;
-    d |= 1u << 4;
-    d |= (bf16 ? 1u : 0u) << 7;
-    d |= (bf16 ? 1u : 0u) << 10;
-    d |= (uint32_t)(tile_n >> 3) << 17;
-    d |= (uint32_t)(256 >> 4) << 24;          // M = 256 across the CTA pair
-    return d;
 }
 
 uint32_t make_idesc(bool bf16) {
@@ -317,19 +262,12 @@ uint32_t make_idesc(bool bf16) {
     d |= (bf16 ? 1u : 0u) << 10;        // B format
     // bits 13/14: no negate; bits 15/16: both operands K-major
     d |= (uint32_t)(tc::TILE_N >> 3) << 17;
-    d |= (uint32_t)(tc::TILE_M >> 4) << 24;
+    d |= (uint32_t)(256 >> 4) << 24;    // M = 256 across the CTA pair
     return d;
 }
 
-}  // namespace
-
-extern "C" {
-
-const char* b200_rank_last_error(void) { return g_last_error.c_str(); }
-int b200_rank_abi_version(void) { return B200_RANK_ABI_VERSION; }
-
-int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_objects, int32_t d, int32_t distance,
-                     int32_t device, int32_t tc_mode, int32_t flags) {
+int create_impl(b200_rank_engine** out, const void* objects, int32_t dtype, int64_t n_objects, int32_t d, int32_t distance,
+                int32_t device, int32_t tc_mode, int32_t flags) {
     if (!out) return fail(B200_E_INVALID, "b200_rank_create: out is NULL");
     *out = nullptr;
     if (n_objects < 0 || d <= 0 || (!objects && n_objects > 0))
@@ -338,6 +276,9 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
     if (distance != B200_DIST_DOT && distance != B200_DIST_COSINE)
         return fail(B200_E_INVALID, "b200_rank_create: distance must be B200_DIST_DOT or B200_DIST_COSINE");
     if (tc_mode < B200_TC_AUTO || tc_mode > B200_TC_OFF) return fail(B200_E_INVALID, "b200_rank_create: bad tc_mode");
+    if (dtype < B200_DT_F32 || dtype > B200_DT_BF16) return fail(B200_E_INVALID, "b200_rank_create: bad dtype");
+    if (dtype != B200_DT_F32 && !(flags & B200_F_OBJECTS_ON_DEVICE))
+        return fail(B200_E_INVALID, "b200_rank_create: 16-bit object factors must be device pointers");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
         return fail(B200_E_CUDA, "b200_rank_create: no CUDA device available (the engine has no CPU fallback)");
@@ -366,44 +307,38 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
         CK(cudaStreamCreateWithFlags(&E->cs, cudaStreamNonBlocking));
         for (auto& e : E->ev) CK(cudaEventCreate(&e));
         for (auto& e : E->evp) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CK(cudaMallocHost(&E->h_pinned, 64));
-        if (flags & B200_F_OBJECTS_ON_DEVICE) {
-            E->obj32_ptr = objects;
-            E->obj32_owned = false;
+        CK(cudaMallocHost(&E->h_pinned, 256));
+        if ((flags & B200_F_OBJECTS_ON_DEVICE) && dtype == B200_DT_F32) {
+            E->obj32_ptr = reinterpret_cast<const float*>(objects);
         } else {
             E->obj32.ensure(sizeof(float) * std::max<int64_t>(n_objects * d, 1));
-            if (n_objects > 0)
-                CK(cudaMemcpyAsync(E->obj32.p, objects, sizeof(float) * n_objects * d, cudaMemcpyHostToDevice, E->st));
+            if (n_objects > 0) {
+                if (dtype == B200_DT_F32) {
+                    CK(cudaMemcpyAsync(E->obj32.p, objects, sizeof(float) * n_objects * d, cudaMemcpyHostToDevice, E->st));
+                } else {
+                    // the caller's stream produced the matrix: order the widening after everything queued on the device
+                    CK(cudaDeviceSynchronize());
+                    widen16_kernel<<<grid_for(n_objects * d, 256), 256, 0, E->st>>>(objects, dtype == B200_DT_BF16 ? 1 : 0, n_objects * d,
+                                                                                   E->obj32.as<float>());
+                    CK(cudaGetLastError());
+                }
+            }
             E->obj32_ptr = E->obj32.as<float>();
         }
         if (tc_mode != B200_TC_OFF && E->d_pad > 1024) tc_mode = B200_TC_OFF;
+        if (tc_mode == B200_TC_AUTO && dtype == B200_DT_BF16) tc_mode = B200_TC_BF16;  // bf16 factors: the tensor-core copy is exact
         prepare_objects(E, tc_mode);
         if (E->tc_dtype != B200_TC_OFF) {
-            TcPlan pl = plan_tc(E->d_pad);
-            if (!pl.ok) {
+            const TcPlan p8 = plan_fused<8>(E->d_pad), p16 = plan_fused<16>(E->d_pad);
+            if (!p8.ok || !p16.ok) {
                 E->tc_dtype = B200_TC_OFF;
             } else {
-                CK(cudaFuncSetAttribute(tc::tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-            }
-            TcPlan pl2 = plan_tc2(E->d_pad, 256), pl2b = plan_tc2(E->d_pad, 128), pl3 = plan_tc3(E->d_pad);
-            if (pl3.ok) CK(cudaFuncSetAttribute(tc::tc3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl3.smem_bytes));
-            TcPlan pl4 = plan_tc4(E->d_pad);  // experimental kernel: never allowed to fail the engine
-            if (pl4.ok) {
-                if (cudaFuncSetAttribute(tc::tc4_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl4.smem_bytes) == cudaSuccess)
-                    E->tc4_ok = true;
-                else
-                    (void)cudaGetLastError();
-            }
-            if (pl2.ok) {
-                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
-                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2.smem_bytes));
-            }
-            if (pl2b.ok) {
-                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<128, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2b.smem_bytes));
-                CK(cudaFuncSetAttribute(tc::tc2_topk_kernel<128, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl2b.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, p8.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p16.smem_bytes));
             }
         }
-        CK(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(rescore_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
     } catch (const CudaError& ce) {
         int rc = fail(ce.e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "b200_rank_create: %s failed at line %d: %s",
                       ce.what, ce.line, cudaGetErrorString(ce.e));
@@ -413,6 +348,390 @@ int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_obj
     }
     *out = E;
     return B200_OK;
+}
+
+// Everything one b200_rank_topk call needs, so that the passes below can be plain functions.
+struct Call {
+    b200_rank_engine* E;
+    const b200_rank_query* q;
+    b200_rank_stats S;
+    cudaStream_t st;
+    int64_t n_rows, n_pos;
+    int k_out, d;
+    // whole-call device views (absolute rows)
+    const float* sub32 = nullptr;
+    const int64_t* rowmap = nullptr;
+    const int64_t* indptr = nullptr;
+    const int32_t* indices = nullptr;
+    const int32_t* wl = nullptr;
+    int32_t *o_ids = nullptr, *o_counts = nullptr;
+    float *o_scores = nullptr, *o_bounds = nullptr;
+    bool wl_gathered = false;
+    bool bf16 = false;
+    int nw = 8;  // epilogue warps of the main pass
+    size_t n_evt = 0;
+    std::vector<int> evt_kind;  // 0 = fused kernel, 1 = selection
+
+    const float* norms() const { return E->distance == B200_DIST_COSINE ? E->obj_norms.as<float>() : nullptr; }
+
+    void time_begin(int kind) {
+        if (E->evt.size() < 2 * (n_evt + 1)) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            E->evt.push_back(a);
+            E->evt.push_back(b);
+        }
+        evt_kind.push_back(kind);
+        CK(cudaEventRecord(E->evt[2 * n_evt], st));
+    }
+    void time_end() {
+        CK(cudaEventRecord(E->evt[2 * n_evt + 1], st));
+        ++n_evt;
+    }
+    void collect_times() {  // after the final synchronisation
+        for (size_t i = 0; i < n_evt; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, E->evt[2 * i], E->evt[2 * i + 1]));
+            if (evt_kind[i] == 0) {
+                S.ms_main += ms;
+                S.n_tc_launches++;
+            } else {
+                S.ms_select += ms;
+            }
+        }
+    }
+};
+
+// Exhaustive fp64 passes over `n_sel` rows (rows_dev == nullptr: rows [0, n_sel) relative to the given base pointers).
+void run_exact(Call& c, const int32_t* rows_dev, int64_t n_sel, const float* sub32, const int64_t* rowmap, const int64_t* indptr,
+               int32_t* o_ids, float* o_scores, int32_t* o_counts, int k_begin, int k_end, bool timed) {
+    b200_rank_engine* E = c.E;
+    const int64_t tiles_total = (c.n_pos + 31) / 32;
+    const int blocks_x = grid_for(n_sel, EX_ROWS);
+    int n_splits = (2 * E->sm_count + blocks_x - 1) / blocks_x;
+    n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_splits, tiles_total / 64));
+    n_splits = std::min(n_splits, 1024);
+    E->part_scores.ensure(sizeof(float) * (size_t)n_splits * n_sel * LIST_LEN);
+    E->part_ids.ensure(sizeof(int32_t) * (size_t)n_splits * n_sel * LIST_LEN);
+    for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+        const int kp = std::min(32, k_end - k0);
+        ExactParams p{};
+        p.subjects = sub32;
+        p.row_map = rowmap;
+        p.rows = rows_dev;
+        p.n_sel_dev = nullptr;
+        p.n_sel = n_sel;
+        p.objects = E->obj32_ptr;
+        p.pos2obj = c.wl;
+        p.n_pos = c.n_pos;
+        p.d = c.d;
+        p.obj_norms = c.norms();
+        p.indptr = indptr;
+        p.indices = c.indices;
+        p.id_off = (int32_t)E->id_offset;
+        p.k_out = c.k_out;
+        p.k0 = k0;
+        p.kp = kp;
+        p.out_ids = o_ids;
+        p.out_scores = o_scores;
+        p.out_counts = o_counts;
+        p.part_scores = E->part_scores.as<float>();
+        p.part_ids = E->part_ids.as<int32_t>();
+        p.part_stride_rows = n_sel;
+        if (timed) c.time_begin(0);
+        exact_topk_kernel<<<dim3(blocks_x, n_splits), EX_THREADS, 0, c.st>>>(p);
+        CK(cudaGetLastError());
+        if (timed) c.time_end();
+        SelectParams sp{};
+        sp.in_scores = E->part_scores.as<float>();
+        sp.in_ids = E->part_ids.as<int32_t>();
+        sp.in_counts = nullptr;
+        sp.n_lists = n_splits;
+        sp.L = LIST_LEN;
+        sp.n_sel = n_sel;
+        sp.list_stride_rows = n_sel;
+        sp.rows = rows_dev;
+        sp.k_out = c.k_out;
+        sp.k0 = k0;
+        sp.kp = kp;
+        sp.out_ids = o_ids;
+        sp.out_scores = o_scores;
+        sp.out_counts = o_counts;
+        merge_select_kernel<<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, 0, c.st>>>(sp);
+        CK(cudaGetLastError());
+        c.S.n_launches += 2;
+    }
+    if (timed) c.S.n_splits = n_splits;
+}
+
+struct TcPass {
+    const int32_t* rows_dev = nullptr;  // nullptr: rows [0, n_sel) of the base pointers below
+    int64_t n_sel = 0;
+    // base pointers: the chunk's slice (rows_dev == nullptr) or the whole call (rows_dev = absolute rows)
+    const float* sub32 = nullptr;
+    const int64_t* rowmap = nullptr;
+    const int64_t* indptr = nullptr;
+    int32_t* o_ids = nullptr;
+    float* o_scores = nullptr;
+    int32_t* o_counts = nullptr;
+    float* o_bounds = nullptr;  // shared-threshold mode: bounds out, no verdict
+    int nw = 8;                 // epilogue warps
+    int kc = 12;                // K' per list
+    int k0 = 0, kp = 0;         // this pass produces entries [k0, k0 + kp)
+    bool wide = false;          // single-pass wide mode (frozen threshold + global append)
+    bool peers = false;         // share thresholds with the other ranks
+    int64_t row0 = 0;           // absolute row of batch row 0 (failure list entries, peer arrays)
+    int32_t* fb_list = nullptr;
+    int32_t* fb_count = nullptr;
+    bool main = false;          // reported in the statistics as the main pass
+};
+
+// One tensor-core candidate pass + fp64 re-score + certificate.  Rows whose certificate fails are appended to `fb_list`.
+void run_tc(Call& c, const TcPass& t) {
+    b200_rank_engine* E = c.E;
+    cudaStream_t st = c.st;
+    const bool bf16 = c.bf16;
+    const int d = c.d;
+    const int nlist = t.nw / 4;
+    const int slots = 64 / nlist;
+    const TcPlan pl = t.nw == 8 ? plan_fused<8>(E->d_pad) : plan_fused<16>(E->d_pad);
+    const int64_t rows_pad = round_up(t.n_sel, 2 * tc::TILE_M);
+    // subjects -> 16-bit, per-row power-of-two scale
+    E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
+    E->row_exp.ensure(sizeof(int32_t) * rows_pad);
+    {
+        const int grid = grid_for(rows_pad * 32, 256);
+        if (!bf16)
+            convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(t.sub32, t.rowmap, t.rows_dev, t.n_sel, rows_pad, d, E->d_pad, nullptr, 0, 1,
+                                                                    E->sub16.as<__half>(), E->row_exp.as<int32_t>());
+        else
+            convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(t.sub32, t.rowmap, t.rows_dev, t.n_sel, rows_pad, d, E->d_pad, nullptr,
+                                                                           0, 0, E->sub16.as<__nv_bfloat16>(), E->row_exp.as<int32_t>());
+        CK(cudaGetLastError());
+        c.S.n_launches++;
+    }
+    // objects: resident 16-bit copy, or a whitelist gather of it
+    const void* obj_base = E->obj16.p;
+    int64_t obj_rows = E->n_obj_pad;
+    if (c.wl) {
+        const int64_t npad = round_up(c.n_pos, tc::HALF_N);
+        if (!c.wl_gathered) {  // shared by every chunk / pass / re-rank of the call
+            c.wl_gathered = true;
+            E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
+            const int chunks = E->d_pad * 2 / 16;
+            gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), c.wl, c.n_pos, npad, chunks,
+                                                                             E->obj16_wl.as<uint4>());
+            CK(cudaGetLastError());
+            c.S.n_launches++;
+        }
+        obj_base = E->obj16_wl.p;
+        obj_rows = npad;
+    }
+    CUtensorMap tm_obj, tm_sub;
+    if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16) || !make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
+        throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled", __LINE__};
+
+    tc::TcParams tp{};
+    tp.kblocks = pl.kblocks;
+    tp.n_stages = pl.n_stages;
+    tp.k_cand = std::min(t.kc, slots);
+    tp.n_rows = t.n_sel;
+    tp.n_pos = c.n_pos;
+    tp.n_row_tiles = (int)(rows_pad / (2 * tc::TILE_M));
+    tp.n_obj_tiles = (int)((c.n_pos + tc::TILE_N - 1) / tc::TILE_N);
+    // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
+    int best_splits = 1;
+    double best_eff = -1.0;
+    const int max_splits = t.wide ? 1 : std::max(1, std::min(16, tp.n_obj_tiles * 2 / 32));
+    const int n_units = E->sm_count / 2;  // CTA pairs working concurrently
+    for (int s = 1; s <= max_splits; ++s) {
+        const double work = (double)tp.n_row_tiles * s;
+        const double waves = std::ceil(work / n_units);
+        const double eff = work / (waves * n_units) - 0.01 * (s - 1);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best_splits = s;
+        }
+    }
+    {
+        const int forced = env_int("B200_TC_SPLITS", 0);  // tuning / test hook
+        if (forced >= 1 && forced <= max_splits) best_splits = forced;
+    }
+    tp.n_splits = best_splits;
+    tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
+    tp.idesc = make_idesc(bf16);
+    tp.pos2obj = c.wl;
+    tp.indptr = t.indptr;
+    tp.indices = c.indices;
+    tp.row_ids = t.rows_dev;
+    if (t.k0 > 0) {  // objects returned by earlier passes are excluded like viewed ones
+        tp.excl = E->excl.as<int32_t>();
+        tp.excl_stride = c.k_out;
+        tp.excl_n = t.k0;
+    }
+    tp.id_off = (int32_t)E->id_offset;
+    const int n_lists = best_splits * nlist;
+    // wide mode: the lists hold ~T = 1.35 k + 40 candidates per row -- the threshold frozen after a fraction q of the stream
+    // is about the (lists x K' - 6)-th best of that fraction, i.e. rank ~ (lists x K' - 6) / q overall
+    int cand_stride = 32;
+    tp.phase1_tiles = 0x7fffffff;
+    if (t.wide) {
+        const double T = env_int("B200_WIDE_T", (int)(1.35 * t.kp + 40));
+        const double rank_frozen = nlist * tp.k_cand - 6;
+        const double qf = std::min(1.0, rank_frozen / T);
+        tp.phase1_tiles = std::max(1, (int)std::ceil(qf * tp.tiles_per_split));
+        cand_stride = (int)round_up((int64_t)(T / nlist * 1.5 + 32), 8);
+        cand_stride = std::min(cand_stride, WIDE_MAX / nlist);
+    }
+    tp.cand_stride = cand_stride;
+    E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * cand_stride);
+    E->cand_ids.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad * cand_stride);
+    E->cand_counts.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad);
+    E->cand_thr.ensure(sizeof(float) * (size_t)n_lists * rows_pad);
+    tp.cand_scores = E->cand_scores.as<float>();
+    tp.cand_ids = E->cand_ids.as<int32_t>();
+    tp.cand_counts = E->cand_counts.as<int32_t>();
+    tp.cand_thr = E->cand_thr.as<float>();
+    tp.rows_pad = rows_pad;
+    tp.debug_mode = env_int("B200_TC_DEBUG", 0);  // measurement hook, results are invalid
+    if (t.peers) {
+        tp.n_peers = E->n_peers;
+        tp.peer_epoch = c.q->peer_epoch;
+        tp.peer_exp = E->obj_exp;
+        tp.peer_row0 = t.row0;
+        tp.peer_pub = E->peer_pub.as<unsigned long long>();
+        for (int i = 0; i < E->n_peers; ++i) tp.peer_in[i] = reinterpret_cast<const unsigned long long*>(E->peer_in[i]);
+    }
+    if (t.main) {
+        c.S.n_splits = best_splits;
+        c.S.k_cand = tp.k_cand;
+        c.S.epi_warps = t.nw;
+        c.S.wide = t.wide ? 1 : 0;
+    }
+    const int n_work = tp.n_row_tiles * tp.n_splits;
+    if (env_int("B200_TC_CAROUSEL", 1) != 0) {  // 0: every work item starts at its first object tile
+        const int n_pairs_run = std::min(n_work, n_units);
+        const int per_pair = (n_work + n_pairs_run - 1) / n_pairs_run;
+        const int64_t n_ints = (int64_t)best_splits + (int64_t)n_pairs_run * per_pair;
+        E->carousel.ensure(sizeof(int32_t) * n_ints);
+        carousel_init_kernel<<<grid_for(n_ints, 256), 256, 0, st>>>(E->carousel.as<int32_t>(), best_splits, tp.tiles_per_split, n_ints);
+        CK(cudaGetLastError());
+        c.S.n_launches++;
+        tp.front = E->carousel.as<int32_t>();
+        tp.starts = tp.front + best_splits;
+        tp.starts_stride = per_pair;
+    }
+    const int grid = 2 * std::min(n_work, n_units);
+    c.time_begin(0);
+    if (t.nw == 8)
+        tc::fused_topk_kernel<8><<<grid, tc::FusedCfg<8>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+    else
+        tc::fused_topk_kernel<16><<<grid, tc::FusedCfg<16>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+    CK(cudaGetLastError());
+    c.time_end();
+    c.S.n_launches++;
+
+    // fp64 re-score of the candidates + certificate
+    SelectParams sp{};
+    sp.in_scores = tp.cand_scores;
+    sp.in_ids = tp.cand_ids;
+    sp.in_counts = tp.cand_counts;
+    sp.in_thr = tp.cand_thr;
+    sp.n_lists = n_lists;
+    sp.L = cand_stride;
+    sp.n_sel = t.n_sel;
+    sp.list_stride_rows = rows_pad;
+    sp.rows = t.rows_dev;
+    sp.k_out = c.k_out;
+    sp.k0 = t.k0;
+    sp.kp = t.kp;
+    sp.out_ids = t.o_ids;
+    sp.out_scores = t.o_scores;
+    sp.out_counts = t.o_counts;
+    sp.subjects = t.sub32;
+    sp.row_map = t.rowmap;
+    sp.objects = E->obj32_ptr;
+    sp.obj_norms = c.norms();
+    sp.d = d;
+    sp.row_exp = E->row_exp.as<int32_t>();
+    sp.obj_exp = E->obj_exp;
+    // |approx - exact| <= eps_rel * |u|_2 * max |i|_2: rounding of both operands (rho each; none for factors that are exact
+    // in the tensor-core type) plus a generous bound on the tensor-core accumulation
+    const double rho = bf16 ? 0.001953125 /*2^-9*/ : 0.00048828125 /*2^-11*/;
+    sp.eps_rel = (float)(2.0 * rho + rho * rho + (double)E->d_pad * 4.76837158e-7 /*2^-21*/ + std::sqrt((double)d) * 1.4551915e-11 /*2^-36*/);
+    sp.max_obj_norm = E->max_obj_norm;
+    sp.fb_count = t.fb_count;
+    sp.fb_rows = t.fb_list;
+    sp.fb_row0 = t.rows_dev ? 0 : t.row0;
+    sp.out_bounds = t.o_bounds;
+    c.time_begin(1);
+    if (t.wide) {
+        rescore_wide_kernel<<<(unsigned)t.n_sel, WIDE_THREADS, (size_t)d * sizeof(float), st>>>(sp);
+    } else {
+        const size_t sel_smem = (size_t)SEL_WARPS * d * sizeof(float);
+        rescore_select_kernel<<<grid_for(t.n_sel, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
+    }
+    CK(cudaGetLastError());
+    c.time_end();
+    c.S.n_launches++;
+}
+
+// Sparse subjects (EASE): SpMM score rows for bounded row chunks + streaming top-k (sparse.cuh).
+void run_sparse(Call& c, const int64_t* sp_indptr, const int32_t* sp_indices, const float* sp_data, int64_t nr, const int64_t* f_indptr,
+                int32_t* o_ids, float* o_scores, int32_t* o_counts) {
+    b200_rank_engine* E = c.E;
+    cudaStream_t st = c.st;
+    if (!E->objT.p && E->n_obj > 0) {  // transposed master copy, built once
+        E->objT.ensure(sizeof(float) * (size_t)E->n_obj * E->d);
+        transpose_kernel<<<dim3((unsigned)grid_for(E->n_obj, 32), (unsigned)grid_for(E->d, 32)), dim3(32, 8), 0, st>>>(E->obj32_ptr, E->n_obj, E->d,
+                                                                                                                  E->objT.as<float>());
+        CK(cudaGetLastError());
+        c.S.n_launches++;
+    }
+    const int64_t rows_max = std::max<int64_t>(1, std::min<int64_t>(nr, ((int64_t)1 << 30) / std::max<int64_t>(4 * c.n_pos, 1)));
+    E->sp_scores.ensure(sizeof(float) * (size_t)rows_max * c.n_pos);
+    for (int64_t b0 = 0; b0 < nr; b0 += rows_max) {
+        const int64_t nb = std::min(rows_max, nr - b0);
+        c.time_begin(0);
+        sparse_scores_kernel<<<dim3((unsigned)nb, (unsigned)grid_for(c.n_pos, SP_BLOCK_COLS)), SP_THREADS, 0, st>>>(
+            sp_indptr + b0, sp_indices, sp_data, E->objT.as<float>(), E->n_obj, E->d, c.wl, c.n_pos, E->sp_scores.as<float>());
+        CK(cudaGetLastError());
+        c.time_end();
+        c.S.n_launches++;
+        for (int k0 = 0; k0 < c.k_out; k0 += 32) {
+            c.time_begin(1);
+            scores_topk_kernel<<<grid_for(nb * 32, 256), 256, 0, st>>>(E->sp_scores.as<float>(), nb, c.n_pos, c.wl, f_indptr ? f_indptr + b0 : nullptr,
+                                                                      c.indices, (int32_t)E->id_offset, c.k_out, k0, std::min(32, c.k_out - k0),
+                                                                      o_ids + b0 * c.k_out, o_scores + b0 * c.k_out, o_counts + b0);
+            CK(cudaGetLastError());
+            c.time_end();
+            c.S.n_launches++;
+        }
+    }
+}
+
+int32_t read_counter(Call& c, const int32_t* dev) {
+    CK(cudaMemcpyAsync(c.E->h_pinned, dev, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+    CK(cudaStreamSynchronize(c.st));
+    return c.E->h_pinned[0];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_rank_last_error(void) { return g_last_error.c_str(); }
+int b200_rank_abi_version(void) { return B200_RANK_ABI_VERSION; }
+
+int b200_rank_create(b200_rank_engine** out, const float* objects, int64_t n_objects, int32_t d, int32_t distance,
+                     int32_t device, int32_t tc_mode, int32_t flags) {
+    return create_impl(out, objects, B200_DT_F32, n_objects, d, distance, device, tc_mode, flags);
+}
+
+int b200_rank_create_ex(b200_rank_engine** out, const void* objects, int32_t dtype, int64_t n_objects, int32_t d, int32_t distance,
+                        int32_t device, int32_t tc_mode, int32_t flags) {
+    return create_impl(out, objects, dtype, n_objects, d, distance, device, tc_mode, flags);
 }
 
 int b200_rank_destroy(b200_rank_engine* E) {
@@ -473,12 +792,58 @@ int b200_rank_set_id_offset(b200_rank_engine* E, int64_t offset) {
     return B200_OK;
 }
 
+int b200_rank_peer_export(b200_rank_engine* E, int64_t max_rows, void* handle_out) {
+    if (!E || !handle_out || max_rows <= 0) return fail(B200_E_INVALID, "b200_rank_peer_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI hands 64-byte handles around");
+    std::lock_guard<std::mutex> lock(E->mu);
+    try {
+        CK(cudaSetDevice(E->device));
+        if (E->peer_pub.p) return fail(B200_E_INVALID, "b200_rank_peer_export: already exported (the peers hold the old handle)");
+        E->peer_pub.ensure(sizeof(unsigned long long) * max_rows);
+        CK(cudaMemset(E->peer_pub.p, 0, E->peer_pub.cap));
+        E->peer_rows = max_rows;
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, E->peer_pub.p));
+        memcpy(handle_out, &h, sizeof(h));
+    } catch (const CudaError& ce) {
+        return fail(B200_E_CUDA, "b200_rank_peer_export: %s failed: %s", ce.what, cudaGetErrorString(ce.e));
+    }
+    return B200_OK;
+}
+
+int b200_rank_peer_import(b200_rank_engine* E, int32_t n_ranks, int32_t self, const void* handles) {
+    if (!E || !handles || n_ranks < 1 || self < 0 || self >= n_ranks) return fail(B200_E_INVALID, "b200_rank_peer_import: bad arguments");
+    if (n_ranks - 1 > tc::MAX_PEERS) return fail(B200_E_UNSUPPORTED, "b200_rank_peer_import: at most %d ranks", tc::MAX_PEERS + 1);
+    std::lock_guard<std::mutex> lock(E->mu);
+    if (!E->peer_pub.p) return fail(B200_E_INVALID, "b200_rank_peer_import: call b200_rank_peer_export first");
+    try {
+        CK(cudaSetDevice(E->device));
+        int n = 0;
+        for (int r = 0; r < n_ranks; ++r) {
+            if (r == self) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, reinterpret_cast<const char*>(handles) + (size_t)r * 64, 64);
+            void* ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            E->peer_in[n++] = ptr;
+        }
+        E->n_peers = n;
+    } catch (const CudaError& ce) {
+        return fail(B200_E_CUDA, "b200_rank_peer_import: %s failed: %s", ce.what, cudaGetErrorString(ce.e));
+    }
+    return B200_OK;
+}
+
 int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stats* stats) {
     if (!E || !q) return fail(B200_E_INVALID, "b200_rank_topk: NULL argument");
     if (q->n_rows < 0) return fail(B200_E_INVALID, "b200_rank_topk: n_rows < 0");
     if (q->k <= 0) return fail(B200_E_INVALID, "b200_rank_topk: k must be positive");
-    if (!q->subjects && !q->subject_ids) return fail(B200_E_INVALID, "b200_rank_topk: neither subjects nor subject_ids given");
-    if (!q->subjects && !E->sub32_res_ptr)
+    const bool sparse_sub = q->sub_indptr != nullptr;
+    if (!sparse_sub && !q->subjects && !q->subject_ids) return fail(B200_E_INVALID, "b200_rank_topk: neither subjects nor subject_ids given");
+    if (sparse_sub && (q->subjects || q->subject_ids)) return fail(B200_E_INVALID, "b200_rank_topk: sparse subjects exclude subjects / subject_ids");
+    if (sparse_sub && E->distance != B200_DIST_DOT)
+        return fail(B200_E_INVALID, "b200_rank_topk: sparse subjects need B200_DIST_DOT (rank_implicit.py:66-67)");
+    if (!sparse_sub && !q->subjects && !E->sub32_res_ptr)
         return fail(B200_E_INVALID, "b200_rank_topk: subject_ids given but b200_rank_set_subjects was never called");
     if (q->subjects && q->subject_ids && q->n_subjects_total <= 0)
         return fail(B200_E_INVALID, "b200_rank_topk: subjects + subject_ids need n_subjects_total");
@@ -488,24 +853,42 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
     if (q->n_rows >= (1ll << 31) - 64) return fail(B200_E_UNSUPPORTED, "b200_rank_topk: more than 2^31 rows per call");
     if ((q->flags & B200_Q_FORCE_EXACT) && (q->flags & B200_Q_FORCE_TC))
         return fail(B200_E_INVALID, "b200_rank_topk: FORCE_EXACT and FORCE_TC are exclusive");
+    const bool in_dev = q->flags & B200_Q_INPUTS_ON_DEVICE;
+    const bool out_dev = q->flags & B200_Q_OUTPUTS_ON_DEVICE;
+    const bool shared = q->flags & B200_Q_SHARED_THRESHOLDS;
+    if (q->subject_dtype != B200_DT_F32 && !(in_dev && q->subjects && !q->subject_ids))
+        return fail(B200_E_INVALID, "b200_rank_topk: 16-bit subjects must be a device matrix in batch order");
+    if (q->subject_dtype < B200_DT_F32 || q->subject_dtype > B200_DT_BF16) return fail(B200_E_INVALID, "b200_rank_topk: bad subject_dtype");
+    if (shared && (!q->out_bounds || q->peer_epoch == 0))
+        return fail(B200_E_INVALID, "b200_rank_topk: B200_Q_SHARED_THRESHOLDS needs out_bounds and peer_epoch >= 1");
+    if (shared && sparse_sub) return fail(B200_E_UNSUPPORTED, "b200_rank_topk: sparse subjects cannot share thresholds");
 
     std::lock_guard<std::mutex> lock(E->mu);
-    b200_rank_stats S;
-    memset(&S, 0, sizeof(S));
+    Call c{};
+    c.E = E;
+    c.q = q;
+    memset(&c.S, 0, sizeof(c.S));
+    b200_rank_stats& S = c.S;
     const int64_t n_rows = q->n_rows;
     const int64_t n_pos = q->whitelist ? q->n_whitelist : E->n_obj;
     const int k_out = (int)std::min<int64_t>(q->k, n_pos);
     S.k_out = k_out;
-    const bool in_dev = q->flags & B200_Q_INPUTS_ON_DEVICE;
-    const bool out_dev = q->flags & B200_Q_OUTPUTS_ON_DEVICE;
     const int d = E->d;
+    c.n_rows = n_rows;
+    c.n_pos = n_pos;
+    c.k_out = k_out;
+    c.d = d;
     if (n_rows == 0 || k_out <= 0) {
         if (stats) *stats = S;
         return B200_OK;
     }
+    if (shared && n_rows > E->peer_rows)
+        return fail(B200_E_INVALID, "b200_rank_topk: %lld rows exceed the %lld exported for threshold sharing", (long long)n_rows,
+                    (long long)E->peer_rows);
     try {
         CK(cudaSetDevice(E->device));
         cudaStream_t st = E->st;
+        c.st = st;
         cudaStream_t user = reinterpret_cast<cudaStream_t>(q->stream);
         // device pointers + NULL stream = CUDA's (legacy) default stream, like every CUDA API: producers / consumers of the
         // buffers on that stream are ordered against the engine stream (torch's current stream is the default stream unless
@@ -521,8 +904,6 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         // Host inputs of a large call are staged in row chunks on a second stream: the copy of chunk c+1 (subject rows / ids,
         // its slice of the CSR filter) and the copy-back of chunk c-1 run while chunk c is being ranked.  Buffers are
         // full-size and addressed by absolute row / nnz offsets, so the kernels see the same layout with or without chunking.
-        const float* sub32 = nullptr;
-        const int64_t* rowmap = nullptr;
         auto stage = [&](DevBuf& buf, const void* src, size_t bytes) -> const void* {  // un-chunked items, main stream
             if (in_dev) return src;
             buf.ensure(std::max<size_t>(bytes, 16));
@@ -531,27 +912,48 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             return buf.p;
         };
         const bool chunk_subjects = q->subjects && !q->subject_ids && !in_dev;  // subject rows arrive in batch order
-        if (q->subjects) {
-            const int64_t rows_in = q->subject_ids ? q->n_subjects_total : n_rows;
-            if (chunk_subjects) {
-                E->sub32.ensure(std::max<size_t>(sizeof(float) * rows_in * d, 16));
-                sub32 = E->sub32.as<float>();
+        const int64_t* sp_indptr = nullptr;
+        const int32_t* sp_indices = nullptr;
+        const float* sp_data = nullptr;
+        if (sparse_sub) {
+            int64_t nnz = 0;
+            if (in_dev) {
+                CK(cudaMemcpyAsync(E->h_pinned, q->sub_indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                memcpy(&nnz, E->h_pinned, sizeof(int64_t));
             } else {
-                sub32 = (const float*)stage(E->sub32, q->subjects, sizeof(float) * rows_in * d);
+                nnz = q->sub_indptr[n_rows];
+            }
+            if (nnz < 0 || (nnz > 0 && (!q->sub_indices || !q->sub_data))) return fail(B200_E_INVALID, "b200_rank_topk: bad sparse subjects");
+            sp_indptr = (const int64_t*)stage(E->sp_indptr, q->sub_indptr, sizeof(int64_t) * (n_rows + 1));
+            sp_indices = (const int32_t*)stage(E->sp_indices, q->sub_indices, sizeof(int32_t) * nnz);
+            sp_data = (const float*)stage(E->sp_data, q->sub_data, sizeof(float) * nnz);
+        } else if (q->subjects) {
+            const int64_t rows_in = q->subject_ids ? q->n_subjects_total : n_rows;
+            if (q->subject_dtype != B200_DT_F32) {
+                E->sub32.ensure(sizeof(float) * rows_in * d);
+                widen16_kernel<<<grid_for(rows_in * d, 256), 256, 0, st>>>(q->subjects, q->subject_dtype == B200_DT_BF16 ? 1 : 0, rows_in * d,
+                                                                           E->sub32.as<float>());
+                CK(cudaGetLastError());
+                S.n_launches++;
+                c.sub32 = E->sub32.as<float>();
+            } else if (chunk_subjects) {
+                E->sub32.ensure(std::max<size_t>(sizeof(float) * rows_in * d, 16));
+                c.sub32 = E->sub32.as<float>();
+            } else {
+                c.sub32 = (const float*)stage(E->sub32, q->subjects, sizeof(float) * rows_in * d);
             }
         } else {
-            sub32 = E->sub32_res_ptr;
+            c.sub32 = E->sub32_res_ptr;
         }
         if (q->subject_ids) {
             if (in_dev) {
-                rowmap = q->subject_ids;
+                c.rowmap = q->subject_ids;
             } else {
                 E->rowmap.ensure(std::max<size_t>(sizeof(int64_t) * n_rows, 16));
-                rowmap = E->rowmap.as<int64_t>();
+                c.rowmap = E->rowmap.as<int64_t>();
             }
         }
-        const int64_t* indptr = nullptr;
-        const int32_t* indices = nullptr;
         if (q->csr_indptr) {
             int64_t nnz = 0;
             if (in_dev) {
@@ -564,18 +966,17 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             if (nnz < 0) return fail(B200_E_INVALID, "b200_rank_topk: csr_indptr[n_rows] < 0");
             if (nnz > 0 && !q->csr_indices) return fail(B200_E_INVALID, "b200_rank_topk: csr_indices is NULL");
             if (in_dev) {
-                indptr = q->csr_indptr;
-                indices = q->csr_indices;
+                c.indptr = q->csr_indptr;
+                c.indices = q->csr_indices;
             } else {
                 E->indptr.ensure(sizeof(int64_t) * (n_rows + 1));
                 E->indices.ensure(std::max<size_t>(sizeof(int32_t) * nnz, 16));
-                indptr = E->indptr.as<int64_t>();
-                indices = E->indices.as<int32_t>();
+                c.indptr = E->indptr.as<int64_t>();
+                c.indices = E->indices.as<int32_t>();
             }
-            if (nnz == 0) indptr = nullptr;  // an all-empty filter is no filter (cf. rank_implicit.py:169-173)
+            if (nnz == 0) c.indptr = nullptr;  // an all-empty filter is no filter (cf. rank_implicit.py:169-173)
         }
-        const int32_t* wl = nullptr;
-        if (q->whitelist) wl = (const int32_t*)stage(E->wl, q->whitelist, sizeof(int32_t) * n_pos);
+        if (q->whitelist) c.wl = (const int32_t*)stage(E->wl, q->whitelist, sizeof(int32_t) * n_pos);
         // host -> device copy of the chunked inputs of rows [r0, r1) on stream `s`
         auto stage_rows = [&](int64_t r0, int64_t r1, cudaStream_t s) {
             if (in_dev) return;
@@ -586,7 +987,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             };
             if (chunk_subjects) h2d(E->sub32.as<float>() + r0 * d, q->subjects + r0 * d, sizeof(float) * (r1 - r0) * d);
             if (q->subject_ids) h2d(E->rowmap.as<int64_t>() + r0, q->subject_ids + r0, sizeof(int64_t) * (r1 - r0));
-            if (indptr) {
+            if (c.indptr) {
                 h2d(E->indptr.as<int64_t>() + r0, q->csr_indptr + r0, sizeof(int64_t) * (r1 - r0 + 1));
                 const int64_t z0 = q->csr_indptr[r0], z1 = q->csr_indptr[r1];
                 if (z1 < z0) throw CudaError{cudaErrorInvalidValue, "csr_indptr must be non-decreasing", __LINE__};
@@ -596,78 +997,49 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         };
 
         // ---------------- outputs
-        int32_t* o_ids;
-        float* o_scores;
-        int32_t* o_counts;
         if (out_dev) {
-            o_ids = q->out_ids;
-            o_scores = q->out_scores;
-            o_counts = q->out_counts;
+            c.o_ids = q->out_ids;
+            c.o_scores = q->out_scores;
+            c.o_counts = q->out_counts;
+            c.o_bounds = shared ? q->out_bounds : nullptr;
         } else {
             E->out_ids.ensure(sizeof(int32_t) * n_rows * k_out);
             E->out_scores.ensure(sizeof(float) * n_rows * k_out);
             E->out_counts.ensure(sizeof(int32_t) * n_rows);
-            o_ids = E->out_ids.as<int32_t>();
-            o_scores = E->out_scores.as<float>();
-            o_counts = E->out_counts.as<int32_t>();
+            c.o_ids = E->out_ids.as<int32_t>();
+            c.o_scores = E->out_scores.as<float>();
+            c.o_counts = E->out_counts.as<int32_t>();
+            if (shared) {
+                E->out_bounds.ensure(sizeof(float) * n_rows);
+                c.o_bounds = E->out_bounds.as<float>();
+            }
         }
         // ---------------- path choice
-        TcPlan pl = plan_tc(E->d_pad);
-        // 2-SM kernel (CTA pairs, cta_group::2) unless disabled or impossible; B200_TC_KERNEL=1 selects the 1-SM kernel
-        // B200_TC_KERNEL: 1 = 1-SM kernel (tc_topk.cuh), 2 = previous 2-SM kernel (tc2_topk.cuh), default 3 = tc3_topk.cuh,
-        // 4 = experimental tc4_topk.cuh for passes with K' <= 16 (everything else of such a call runs on tc3)
-        bool use_2sm = (E->sm_count % 2 == 0);
-        int kernel_gen = 3;
-        if (const char* env = getenv("B200_TC_KERNEL")) {
-            kernel_gen = atoi(env);
-            use_2sm = use_2sm && kernel_gen != 1;
-        }
-        // tile width of the 2-SM kernel: 256 objects x 2 TMEM buffers (default) or 128 x 4 (B200_TC_TILE=128)
-        int tile2_n = 256;
-        if (const char* env = getenv("B200_TC_TILE")) tile2_n = atoi(env) == 128 ? 128 : 256;
-        bool use_gen3 = use_2sm && kernel_gen != 2 && tile2_n == 256;
-        if (use_gen3) {
-            TcPlan pl3 = plan_tc3(E->d_pad);
-            if (pl3.ok)
-                pl = pl3;
-            else
-                use_gen3 = false;
-        }
-        const TcPlan pl4 = plan_tc4(E->d_pad);
-        const bool use_gen4 = use_gen3 && kernel_gen == 4 && pl4.ok && E->tc4_ok;
-        if (use_2sm && !use_gen3) {
-            TcPlan pl2 = plan_tc2(E->d_pad, tile2_n);
-            if (pl2.ok)
-                pl = pl2;
-            else
-                use_2sm = false;
-        }
-        // Candidates kept per list by the tensor-core pass (K' >= k; the surplus is the certificate's safety margin).
-        // 1-SM kernel: one list per row.  2-SM kernel: two lists per row (one per column half), so a small surplus per
-        // list already gives ~2k candidates; rows where (nearly) all of the top-k fall into one half fail the
+        // Candidates kept per list by the tensor-core pass (K' >= k / lists; the surplus is the certificate's safety margin).
+        // A row has 2 (8 epilogue warps) or 4 (16) lists, one per column group of the tile stream, so a small surplus per
+        // list already gives ~2k candidates; rows where (nearly) all of the top-k fall into one column group fail the
         // certificate and take the second-chance pass.  Inserts, the dominant epilogue cost, scale with K'.
+        c.bf16 = E->tc_dtype == B200_TC_BF16;
+        c.nw = env_int("B200_EPI_WARPS", 8) == 16 ? 16 : 8;
+        const bool wide = k_out > 24 && k_out <= 128 && env_int("B200_WIDE", 1) != 0;
         int k_cand = 0;
-        const bool bf16_tc = E->tc_dtype == B200_TC_BF16;
-        if (use_gen4 && k_out <= 24) {
-            // four lists per row: a list may be SHORTER than k (the certificate only needs the k-th exact score above every
-            // full list's minimum); rows whose top-k crowd into one column quarter take the second-chance pass
-            k_cand = std::min(tc::T4_SLOTS, (k_out <= 10 ? 8 : k_out <= 16 ? 12 : 16) + (bf16_tc ? 2 : 0));
-        } else if (use_2sm) {
-            const int surplus = bf16_tc ? std::max(6, k_out / 2) : std::max(2, k_out / 4);
-            if (k_out <= 24) k_cand = std::min(32, k_out + surplus);
-            else if (k_out <= 128) k_cand = 25;  // multi-pass, see below
-        } else {
-            if (k_out <= 10 && !bf16_tc)
-                k_cand = 16;
-            else if (k_out <= 128)
-                k_cand = 32;
+        if (k_out <= 24) {
+            if (c.nw == 16) {
+                // four lists per row: a list may be SHORTER than k (the certificate only needs the k-th exact score above every
+                // list's threshold); rows whose top-k crowd into one column quarter take the second-chance pass
+                k_cand = std::min(16, (k_out <= 10 ? 8 : k_out <= 16 ? 12 : 16) + (c.bf16 ? 2 : 0));
+            } else {
+                const int surplus = c.bf16 ? std::max(6, k_out / 2) : std::max(2, k_out / 4);
+                k_cand = std::min(32, k_out + surplus);
+            }
+        } else if (k_out <= 128) {
+            k_cand = wide ? (c.nw == 16 ? 12 : 24) : (c.bf16 ? 30 : 25);  // wide: adaptive lists of phase 1;  else passes of 20
         }
-        if (const char* env = getenv("B200_TC_KCAND")) {  // tuning hook
-            const int forced = atoi(env);
-            if ((forced >= k_out || use_gen4) && forced >= 4 && forced <= 32) k_cand = forced;
+        {
+            const int forced = env_int("B200_TC_KCAND", 0);  // tuning hook
+            if (forced >= 4 && forced <= 32 && (forced >= k_out || c.nw == 16 || wide)) k_cand = forced;
         }
-        bool use_tc = E->tc_dtype != B200_TC_OFF && pl.ok && k_cand > 0 && !(q->flags & B200_Q_FORCE_EXACT) &&
-                      n_pos >= (int64_t)k_cand * 4;
+        bool use_tc = !sparse_sub && E->tc_dtype != B200_TC_OFF && k_cand > 0 && !(q->flags & B200_Q_FORCE_EXACT) && n_pos >= (int64_t)k_cand * 4;
         if (use_tc && !(q->flags & B200_Q_FORCE_TC)) {
             // tiny problems are cheaper (and exercised) on the exhaustive kernel
             if ((double)n_rows * (double)n_pos < 4.0e6) use_tc = false;
@@ -677,329 +1049,129 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         if ((q->flags & B200_Q_FORCE_TC) && !use_tc)
             return fail(B200_E_UNSUPPORTED, "b200_rank_topk: tensor-core path unavailable (tc_dtype=%d, k=%d, d_pad=%d, n_pos=%lld)",
                         E->tc_dtype, k_out, E->d_pad, (long long)n_pos);
+        const bool peers = shared && use_tc;  // (zero peers: the same protocol, nothing to adopt)
+        if (shared && use_tc && k_out > 24) return fail(B200_E_UNSUPPORTED, "b200_rank_topk: B200_Q_SHARED_THRESHOLDS needs k <= 24");
 
-        // ---------------- rank the rows of one chunk (the parameters shadow the whole-call values of the same names)
-        bool wl_gathered = false;  // the whitelist gather of the 16-bit objects is shared by all chunks / passes of a call
-        auto compute_rows = [&](int64_t n_rows, const float* sub32, const int64_t* rowmap, const int64_t* indptr, int32_t* o_ids,
-                                float* o_scores, int32_t* o_counts) {
-            init_outputs_kernel<<<grid_for(std::max<int64_t>(n_rows * k_out, n_rows), 256), 256, 0, st>>>(o_ids, o_scores, o_counts,
-                                                                                                       n_rows, k_out);
+        // failure lists (absolute rows) + counters: [fb1 | fb2 | fbA | fbB | counters]
+        E->fb_rows.ensure(sizeof(int32_t) * (4 * n_rows + 16));
+        int32_t* fb1 = E->fb_rows.as<int32_t>();
+        int32_t* fb2 = fb1 + n_rows;
+        int32_t* fbA = fb2 + n_rows;
+        int32_t* fbB = fbA + n_rows;
+        int32_t* cnt = fbB + n_rows;
+        CK(cudaMemsetAsync(cnt, 0, 16 * sizeof(int32_t), st));
+        if (wide || (use_tc && k_out > 24)) E->excl.ensure(sizeof(int32_t) * (size_t)n_rows * k_out);
+
+        // ---------------- main pass over the rows of one chunk
+        auto main_pass = [&](int64_t r0, int64_t r1) {
+            const int64_t nr = r1 - r0;
+            int32_t* oi = c.o_ids + r0 * k_out;
+            float* os = c.o_scores + r0 * k_out;
+            int32_t* oc = c.o_counts + r0;
+            init_outputs_kernel<<<grid_for(std::max<int64_t>(nr * k_out, nr), 256), 256, 0, st>>>(oi, os, oc, nr, k_out);
             CK(cudaGetLastError());
             S.n_launches++;
-
-            const bool cosine = E->distance == B200_DIST_COSINE;
-            const float* norms = cosine ? E->obj_norms.as<float>() : nullptr;
-
-            // exhaustive fp64 passes over `n_sel` rows (rows_dev == nullptr: all rows)
-            auto run_exact = [&](const int32_t* rows_dev, int64_t n_sel, bool timed, int k_begin, int k_end) {
-                const int64_t tiles_total = (n_pos + 31) / 32;
-                const int blocks_x = grid_for(n_sel, EX_ROWS);
-                int n_splits = (2 * E->sm_count + blocks_x - 1) / blocks_x;
-                n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(n_splits, tiles_total / 64));
-                n_splits = std::min(n_splits, 1024);
-                E->part_scores.ensure(sizeof(float) * (size_t)n_splits * n_sel * LIST_LEN);
-                E->part_ids.ensure(sizeof(int32_t) * (size_t)n_splits * n_sel * LIST_LEN);
-                for (int k0 = k_begin; k0 < k_end; k0 += 32) {
-                    const int kp = std::min(32, k_end - k0);
-                    ExactParams p{};
-                    p.subjects = sub32;
-                    p.row_map = rowmap;
-                    p.rows = rows_dev;
-                    p.n_sel_dev = nullptr;
-                    p.n_sel = n_sel;
-                    p.objects = E->obj32_ptr;
-                    p.pos2obj = wl;
-                    p.n_pos = n_pos;
-                    p.d = d;
-                    p.obj_norms = norms;
-                    p.indptr = indptr;
-                    p.indices = indices;
-                    p.id_off = (int32_t)E->id_offset;
-                    p.k_out = k_out;
-                    p.k0 = k0;
-                    p.kp = kp;
-                    p.out_ids = o_ids;
-                    p.out_scores = o_scores;
-                    p.out_counts = o_counts;
-                    p.part_scores = E->part_scores.as<float>();
-                    p.part_ids = E->part_ids.as<int32_t>();
-                    p.part_stride_rows = n_sel;
-                    if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[2], st));
-                    exact_topk_kernel<<<dim3(blocks_x, n_splits), EX_THREADS, 0, st>>>(p);
-                    CK(cudaGetLastError());
-                    if (timed && k0 == k_begin) CK(cudaEventRecord(E->ev[3], st));
-                    SelectParams sp{};
-                    sp.in_scores = E->part_scores.as<float>();
-                    sp.in_ids = E->part_ids.as<int32_t>();
-                    sp.in_counts = nullptr;
-                    sp.n_lists = n_splits;
-                    sp.L = LIST_LEN;
-                    sp.n_sel = n_sel;
-                    sp.list_stride_rows = n_sel;
-                    sp.rows = rows_dev;
-                    sp.k_out = k_out;
-                    sp.k0 = k0;
-                    sp.kp = kp;
-                    sp.out_ids = o_ids;
-                    sp.out_scores = o_scores;
-                    sp.out_counts = o_counts;
-                    select_kernel<false><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
-                    CK(cudaGetLastError());
-                    S.n_launches += 2;
-                }
-                S.n_splits = n_splits;
-            };
-
-            // One tensor-core candidate pass + fp64 re-score + certificate over `n_sel` rows (rows_dev == nullptr: all rows).
-            // Rows whose certificate fails are appended to `fb_list`; returns their number.
-            auto run_tc = [&](const int32_t* rows_dev, int64_t n_sel, int kc, int k0, int kp, int32_t* fb_list, int32_t* fb_count,
-                              bool timed) -> int64_t {
-                const bool bf16 = E->tc_dtype == B200_TC_BF16;
-                const bool g4 = use_gen4 && kc <= tc::T4_SLOTS;  // this pass on the experimental kernel
-                const TcPlan& plx = g4 ? pl4 : pl;
-                const int rows_per_cta = plx.s_sub * tc::TILE_M;
-                const int64_t rows_pad = round_up(n_sel, rows_per_cta);
-                // subjects -> 16-bit, per-row power-of-two scale
-                E->sub16.ensure((size_t)rows_pad * E->d_pad * 2);
-                E->row_exp.ensure(sizeof(int32_t) * rows_pad);
-                {
-                    const int grid = grid_for(rows_pad * 32, 256);
-                    if (!bf16)
-                        convert_rows_kernel<__half, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad, nullptr,
-                                                                                0, 1, E->sub16.as<__half>(), E->row_exp.as<int32_t>());
-                    else
-                        convert_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(sub32, rowmap, rows_dev, n_sel, rows_pad, d, E->d_pad,
-                                                                                       nullptr, 0, 0, E->sub16.as<__nv_bfloat16>(),
-                                                                                       E->row_exp.as<int32_t>());
-                    CK(cudaGetLastError());
-                    S.n_launches++;
-                }
-                // objects: resident 16-bit copy, or a whitelist gather of it
-                const int obj_box_rows = use_2sm ? tile2_n / 2 : 128;  // object rows one CTA loads per ring block
-                const void* obj_base = E->obj16.p;
-                int64_t obj_rows = E->n_obj_pad;
-                if (wl) {
-                    const int64_t npad = round_up(n_pos, tc::TILE_N);
-                    if (!wl_gathered) {  // shared by every chunk / pass / re-rank of the call
-                        wl_gathered = true;
-                        E->obj16_wl.ensure((size_t)npad * E->d_pad * 2);
-                        const int chunks = E->d_pad * 2 / 16;
-                        gather_rows16_kernel<<<grid_for(npad * chunks, 256), 256, 0, st>>>(E->obj16.as<uint4>(), wl, n_pos, npad, chunks,
-                                                                                         E->obj16_wl.as<uint4>());
-                        CK(cudaGetLastError());
-                        S.n_launches++;
-                    }
-                    obj_base = E->obj16_wl.p;
-                    obj_rows = npad;
-                }
-                CUtensorMap tm_obj, tm_sub;
-                if (!make_tensor_map(&tm_obj, obj_base, obj_rows, E->d_pad, bf16, obj_box_rows) ||
-                    !make_tensor_map(&tm_sub, E->sub16.p, rows_pad, E->d_pad, bf16))
-                    throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled", __LINE__};
-
-                tc::TcParams tp{};
-                tp.s_sub = plx.s_sub;
-                tp.kblocks = plx.kblocks;
-                tp.n_stages = plx.n_stages;
-                tp.k_cand = kc;
-                tp.n_rows = n_sel;
-                tp.n_pos = n_pos;
-                tp.n_row_tiles = (int)(rows_pad / rows_per_cta);
-                const int tile_n = use_2sm ? tile2_n : tc::TILE_N;
-                const int lists_per_split = g4 ? 4 : use_2sm ? 2 : 1;
-                tp.n_obj_tiles = (int)((n_pos + tile_n - 1) / tile_n);
-                // object splits: fill the machine when there are few row tiles, even out the last wave otherwise
-                int best_splits = 1;
-                double best_eff = -1.0;
-                const int max_splits = std::max(1, std::min(16, tp.n_obj_tiles * (tile_n / 128) / 32));
-                const int n_units = use_2sm ? E->sm_count / 2 : E->sm_count;  // CTAs or CTA pairs working concurrently
-                for (int s = 1; s <= max_splits; ++s) {
-                    const double work = (double)tp.n_row_tiles * s;
-                    const double waves = std::ceil(work / n_units);
-                    const double eff = work / (waves * n_units) - 0.01 * (s - 1);
-                    if (eff > best_eff + 1e-9) {
-                        best_eff = eff;
-                        best_splits = s;
-                    }
-                }
-                if (const char* env = getenv("B200_TC_SPLITS")) {  // tuning / test hook
-                    const int forced = atoi(env);
-                    if (forced >= 1 && forced <= max_splits) best_splits = forced;
-                }
-                tp.n_splits = best_splits;
-                tp.tiles_per_split = (tp.n_obj_tiles + best_splits - 1) / best_splits;
-                tp.idesc = use_2sm ? make_idesc2(bf16, tile2_n) : make_idesc(bf16);
-                tp.pos2obj = wl;
-                tp.indptr = indptr;
-                tp.indices = indices;
-                tp.row_ids = rows_dev;
-                if (k0 > 0) {  // objects returned by earlier passes are excluded like viewed ones
-                    tp.excl = E->excl.as<int32_t>();
-                    tp.excl_stride = k_out;
-                    tp.excl_n = k0;
-                }
-                tp.id_off = (int32_t)E->id_offset;
-                const int n_lists = best_splits * lists_per_split;
-                E->cand_scores.ensure(sizeof(float) * (size_t)n_lists * rows_pad * 32);
-                E->cand_ids.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad * 32);
-                E->cand_counts.ensure(sizeof(int32_t) * (size_t)n_lists * rows_pad);
-                tp.cand_scores = E->cand_scores.as<float>();
-                tp.cand_ids = E->cand_ids.as<int32_t>();
-                tp.cand_counts = E->cand_counts.as<int32_t>();
-                tp.rows_pad = rows_pad;
-                if (const char* env = getenv("B200_TC_DEBUG")) tp.debug_mode = atoi(env);  // measurement hook, results are invalid
-                if (timed) S.n_splits = best_splits;
-                const int n_work = tp.n_row_tiles * tp.n_splits;
-                bool carousel = use_2sm;  // B200_TC_CAROUSEL=0 disables it (every work item then starts at its first object tile)
-                if (const char* env = getenv("B200_TC_CAROUSEL")) carousel = carousel && atoi(env) != 0;
-                if (carousel) {
-                    const int n_pairs_run = std::min(n_work, n_units);
-                    const int per_pair = (n_work + n_pairs_run - 1) / n_pairs_run;
-                    const size_t n_ints = (size_t)best_splits + (size_t)n_pairs_run * per_pair;
-                    E->carousel.ensure(sizeof(int32_t) * n_ints);
-                    std::vector<int32_t> init(best_splits);
-                    for (int sidx = 0; sidx < best_splits; ++sidx) init[sidx] = sidx * tp.tiles_per_split;
-                    CK(cudaMemsetAsync(E->carousel.p, 0xFF, sizeof(int32_t) * n_ints, st));
-                    CK(cudaMemcpyAsync(E->carousel.p, init.data(), sizeof(int32_t) * best_splits, cudaMemcpyHostToDevice, st));
-                    CK(cudaStreamSynchronize(st));  // `init` is a stack buffer
-                    tp.front = E->carousel.as<int32_t>();
-                    tp.starts = tp.front + best_splits;
-                    tp.starts_stride = per_pair;
-                }
-                if (timed) CK(cudaEventRecord(E->ev[2], st));
-                if (use_2sm) {
-                    const int grid = 2 * std::min(n_work, n_units);
-                    bool stage_regs = true;  // B200_TC_STAGE=0: scan straight from TMEM in 32-column chunks
-                    if (const char* env = getenv("B200_TC_STAGE")) stage_regs = atoi(env) != 0;
-                    if (g4)
-                        tc::tc4_topk_kernel<<<grid, tc::T4_THREADS, plx.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                    else if (use_gen3)
-                        tc::tc3_topk_kernel<<<grid, tc::T3_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                    else if (tile2_n == 256 && stage_regs)
-                        tc::tc2_topk_kernel<256, 2, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                    else if (tile2_n == 256)
-                        tc::tc2_topk_kernel<256, 2, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                    else if (stage_regs)
-                        tc::tc2_topk_kernel<128, 4, true><<<grid, tc::Tc2Threads<true>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                    else
-                        tc::tc2_topk_kernel<128, 4, false><<<grid, tc::Tc2Threads<false>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                } else {
-                    const int grid = std::min(n_work, n_units);
-                    tc::tc_topk_kernel<<<grid, tc::NUM_THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-                }
-                CK(cudaGetLastError());
-                if (timed) CK(cudaEventRecord(E->ev[3], st));
-                S.n_launches++;
-
-                // fp64 re-score of the candidates + certificate
-                CK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), st));
-                SelectParams sp{};
-                sp.in_scores = tp.cand_scores;
-                sp.in_ids = tp.cand_ids;
-                sp.in_counts = tp.cand_counts;
-                sp.n_lists = n_lists;
-                sp.L = 32;
-                sp.n_sel = n_sel;
-                sp.list_stride_rows = rows_pad;
-                sp.rows = rows_dev;
-                sp.k_out = k_out;
-                sp.k0 = k0;
-                sp.kp = kp;
-                sp.out_ids = o_ids;
-                sp.out_scores = o_scores;
-                sp.out_counts = o_counts;
-                sp.subjects = sub32;
-                sp.row_map = rowmap;
-                sp.objects = E->obj32_ptr;
-                sp.obj_norms = norms;
-                sp.d = d;
-                sp.k_cand = kc;
-                sp.row_exp = E->row_exp.as<int32_t>();
-                sp.obj_exp = E->obj_exp;
-                const double rho = bf16 ? 0.001953125 /*2^-9*/ : 0.00048828125 /*2^-11*/;
-                sp.eps_rel = (float)(2.0 * rho + rho * rho + (double)E->d_pad * 4.76837158e-7 /*2^-21*/ +
-                                     std::sqrt((double)d) * 1.4551915e-11 /*2^-36*/);
-                sp.max_obj_norm = E->max_obj_norm;
-                sp.fb_count = fb_count;
-                sp.fb_rows = fb_list;
-                const size_t sel_smem = (size_t)SEL_WARPS * d * sizeof(float);
-                select_kernel<true><<<grid_for(n_sel, SEL_WARPS), SEL_WARPS * 32, sel_smem, st>>>(sp);
-                CK(cudaGetLastError());
-                S.n_launches++;
-                CK(cudaMemcpyAsync(E->h_pinned, fb_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (timed) {
-                    float ms = 0.f;
-                    CK(cudaEventElapsedTime(&ms, E->ev[2], E->ev[3]));
-                    S.ms_main += ms;
-                }
-                return (int64_t)E->h_pinned[0];
-            };
-
-            if (!use_tc) {
+            const float* sub = (c.sub32 && !c.rowmap) ? c.sub32 + r0 * d : c.sub32;
+            const int64_t* rm = c.rowmap ? c.rowmap + r0 : nullptr;
+            const int64_t* ip = c.indptr ? c.indptr + r0 : nullptr;
+            if (sparse_sub) {
+                S.path = 2;
+                run_sparse(c, sp_indptr + r0, sp_indices, sp_data, nr, ip, oi, os, oc);
+            } else if (!use_tc) {
                 S.path = 0;
-                run_exact(nullptr, n_rows, true, 0, k_out);
+                run_exact(c, nullptr, nr, sub, rm, ip, oi, os, oc, 0, k_out, true);
+                if (c.o_bounds) {  // exhaustive lists: nothing was discarded
+                    fill_f32_kernel<<<grid_for(nr, 256), 256, 0, st>>>(c.o_bounds + r0, nr, -INFINITY);
+                    CK(cudaGetLastError());
+                }
             } else {
                 S.path = 1;
                 S.tc_dtype = E->tc_dtype;
-                S.k_cand = k_cand;
-                // two failure lists of n_rows entries + two counters
-                E->fb_rows.ensure(sizeof(int32_t) * (2 * n_rows + 2));
-                int32_t* fb1 = E->fb_rows.as<int32_t>();
-                int32_t* fb2 = fb1 + n_rows;
-                int32_t* cnt = fb2 + n_rows;
-                // k <= 24: one pass.  Larger k: passes of `k_pass` results; every pass is certified (or re-ranked) on its own and
-                // the ids returned so far are excluded from the next pass exactly like viewed objects, so the concatenation of
-                // the passes is the exact top-k in order.
-                const int k_pass = k_out <= 24 ? k_out : 20;
-                const int kc_pass = k_out <= 24 ? k_cand : (use_2sm ? (bf16_tc ? 30 : 25) : 32);
-                if (k_out > 24) E->excl.ensure(sizeof(int32_t) * (size_t)n_rows * k_out);
-                int64_t total_fb = 0, total_exact = 0;
-                for (int k0 = 0; k0 < k_out; k0 += k_pass) {
-                    const int kp = std::min(k_pass, k_out - k0);
-                    const int kc = std::min(32, std::max(kc_pass - (k_pass - kp), kp));
-                    if (k0 > 0) {
-                        build_exclusion_kernel<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(o_ids, n_rows, k_out, k0, (int32_t)E->id_offset,
-                                                                                          E->excl.as<int32_t>());
-                        CK(cudaGetLastError());
-                        S.n_launches++;
-                    }
-                    int32_t* f1 = fb1;
-                    int64_t n_fb = run_tc(nullptr, n_rows, kc, k0, kp, f1, cnt, k0 == 0);
-                    total_fb += n_fb;
-                    // second chance for rows whose certificate failed: same pass with the widest candidate lists (32), which
-                    // only near-exact ties survive; whatever is left goes to the exhaustive fp64 kernel
-                    if (n_fb > 0 && kc < 32) {
-                        n_fb = run_tc(f1, n_fb, 32, k0, kp, fb2, cnt + 1, false);
-                        f1 = fb2;
-                    }
-                    total_exact += n_fb;
-                    if (n_fb > 0) {
-                        const int tc_splits = S.n_splits;
-                        run_exact(f1, n_fb, false, k0, k0 + kp);
-                        S.n_splits = tc_splits;  // report the splits of the main kernel, not of the re-rank
-                    }
-                }
-                S.n_fallback_rows += total_fb;
-                S.n_exact_rows += total_exact;
+                TcPass t;
+                t.n_sel = nr;
+                t.sub32 = sub;
+                t.rowmap = rm;
+                t.indptr = ip;
+                t.o_ids = oi;
+                t.o_scores = os;
+                t.o_counts = oc;
+                t.o_bounds = c.o_bounds ? c.o_bounds + r0 : nullptr;
+                t.nw = c.nw;
+                t.kc = k_cand;
+                t.row0 = r0;
+                t.fb_list = fb1;
+                t.fb_count = cnt;
+                t.main = true;
+                t.peers = peers;
+                t.k0 = 0;
+                t.kp = k_out;
+                t.wide = wide;
+                run_tc(c, t);
             }
-
             if (E->id_offset != 0) {
-                add_offset_kernel<<<grid_for(n_rows * k_out, 256), 256, 0, st>>>(o_ids, n_rows * k_out, (int32_t)E->id_offset);
+                add_offset_kernel<<<grid_for(nr * k_out, 256), 256, 0, st>>>(oi, nr * k_out, (int32_t)E->id_offset);
                 CK(cudaGetLastError());
                 S.n_launches++;
             }
-            if (!use_tc) {  // (the tensor-core path reads its kernel time after the synchronisation of every pass)
-                CK(cudaStreamSynchronize(st));
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, E->ev[2], E->ev[3]));
-                S.ms_main += ms;
+        };
+
+        // Re-rank `n_sel` rows (absolute row numbers in `rows`) without any shortcut that could fail again unnoticed:
+        // k <= 24: one pass with the widest lists (32 slots, 8-warp kernel), then the exhaustive kernel for what still fails;
+        // k  > 24: certified passes of 20 results with exclusion lists, each followed by its own wide-list pass and the
+        // exhaustive kernel.  Results are written with LOCAL ids; the caller applies the id offset.
+        auto rerank_rows = [&](const int32_t* rows, int64_t n_sel) {
+            init_rows_kernel<<<grid_for(n_sel * k_out, 256), 256, 0, st>>>(c.o_ids, c.o_scores, c.o_counts, rows, n_sel, k_out);
+            CK(cudaGetLastError());
+            S.n_launches++;
+            const int k_pass = k_out <= 24 ? k_out : 20;
+            const int kc_pass = k_out <= 24 ? 32 : (c.bf16 ? 30 : 25);
+            for (int k0 = 0; k0 < k_out; k0 += k_pass) {
+                const int kp = std::min(k_pass, k_out - k0);
+                if (k0 > 0) {
+                    build_exclusion_kernel<<<grid_for(n_sel * 32, 256), 256, 0, st>>>(c.o_ids, rows, n_sel, k_out, k0, (int32_t)E->id_offset,
+                                                                                     E->excl.as<int32_t>());
+                    CK(cudaGetLastError());
+                    S.n_launches++;
+                }
+                CK(cudaMemsetAsync(cnt + 2, 0, 2 * sizeof(int32_t), st));
+                TcPass t;
+                t.rows_dev = rows;
+                t.n_sel = n_sel;
+                t.sub32 = c.sub32;
+                t.rowmap = c.rowmap;
+                t.indptr = c.indptr;
+                t.o_ids = c.o_ids;
+                t.o_scores = c.o_scores;
+                t.o_counts = c.o_counts;
+                t.nw = 8;
+                t.kc = std::min(32, std::max(kc_pass - (k_pass - kp), kp));
+                t.k0 = k0;
+                t.kp = kp;
+                t.fb_list = fbA;
+                t.fb_count = cnt + 2;
+                run_tc(c, t);
+                int64_t n_fb = read_counter(c, cnt + 2);
+                const int32_t* f = fbA;
+                if (n_fb > 0 && t.kc < 32) {  // the pass's own second chance: widest lists
+                    TcPass t2 = t;
+                    t2.rows_dev = fbA;
+                    t2.n_sel = n_fb;
+                    t2.kc = 32;
+                    t2.fb_list = fbB;
+                    t2.fb_count = cnt + 3;
+                    run_tc(c, t2);
+                    n_fb = read_counter(c, cnt + 3);
+                    f = fbB;
+                }
+                S.n_exact_rows += n_fb;
+                if (n_fb > 0) run_exact(c, f, n_fb, c.sub32, c.rowmap, c.indptr, c.o_ids, c.o_scores, c.o_counts, k0, k0 + kp, false);
             }
         };
 
         // ---------------- chunk pipeline
+        const bool multipass_main = use_tc && k_out > 24 && !wide;
         int64_t chunk = n_rows;
-        if (!in_dev && use_tc) {
+        if (!in_dev && use_tc && !multipass_main) {
             const int64_t wave = (int64_t)(E->sm_count / 2) * 256;  // subject rows one wave of CTA pairs works on
             int64_t want = 8 * wave;
             if (const char* env = getenv("B200_CHUNK_ROWS")) want = std::max<int64_t>(256, atoll(env));  // test hook
@@ -1015,25 +1187,91 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         stage_rows(0, std::min(chunk, n_rows), cs);
         CK(cudaEventRecord(E->evp[0], cs));
         CK(cudaEventRecord(E->ev[1], cs));
-        for (int64_t c = 0; c < n_chunks; ++c) {
-            const int64_t r0 = c * chunk, r1 = std::min(n_rows, r0 + chunk);
-            if (c + 1 < n_chunks) {
-                stage_rows(r1, std::min(n_rows, r1 + chunk), cs);
-                CK(cudaEventRecord(E->evp[(c + 1) & 1], cs));
+        auto copy_back = [&](int64_t r0, int64_t r1, cudaStream_t s) {
+            CK(cudaMemcpyAsync(q->out_ids + r0 * k_out, c.o_ids + r0 * k_out, sizeof(int32_t) * (r1 - r0) * k_out, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(q->out_scores + r0 * k_out, c.o_scores + r0 * k_out, sizeof(float) * (r1 - r0) * k_out, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(q->out_counts + r0, c.o_counts + r0, sizeof(int32_t) * (r1 - r0), cudaMemcpyDeviceToHost, s));
+            S.d2h_bytes += (int64_t)((r1 - r0) * k_out * 8 + (r1 - r0) * 4);
+            if (shared) {
+                CK(cudaMemcpyAsync(q->out_bounds + r0, c.o_bounds + r0, sizeof(float) * (r1 - r0), cudaMemcpyDeviceToHost, s));
+                S.d2h_bytes += (int64_t)(r1 - r0) * 4;
             }
-            if (n_chunks > 1) CK(cudaStreamWaitEvent(st, E->evp[c & 1], 0));
-            compute_rows(r1 - r0, (sub32 && !rowmap) ? sub32 + r0 * d : sub32, rowmap ? rowmap + r0 : nullptr, indptr ? indptr + r0 : nullptr,
-                         o_ids + r0 * k_out, o_scores + r0 * k_out, o_counts + r0);
-            if (c + 1 == n_chunks) CK(cudaEventRecord(E->ev[4], st));
+        };
+        for (int64_t ci = 0; ci < n_chunks; ++ci) {
+            const int64_t r0 = ci * chunk, r1 = std::min(n_rows, r0 + chunk);
+            if (ci + 1 < n_chunks) {
+                stage_rows(r1, std::min(n_rows, r1 + chunk), cs);
+                CK(cudaEventRecord(E->evp[(ci + 1) & 1], cs));
+            }
+            if (n_chunks > 1) CK(cudaStreamWaitEvent(st, E->evp[ci & 1], 0));
+            if (multipass_main) {
+                // every row takes the certified multi-pass route (tuning / test hook B200_WIDE=0)
+                S.path = 1;
+                S.tc_dtype = E->tc_dtype;
+                S.k_cand = k_cand;
+                S.epi_warps = 8;
+                iota_kernel<<<grid_for(n_rows, 256), 256, 0, st>>>(fb1, n_rows);
+                CK(cudaGetLastError());
+                rerank_rows(fb1, n_rows);
+                if (E->id_offset != 0) {
+                    add_offset_kernel<<<grid_for(n_rows * k_out, 256), 256, 0, st>>>(c.o_ids, n_rows * k_out, (int32_t)E->id_offset);
+                    CK(cudaGetLastError());
+                }
+            } else {
+                main_pass(r0, r1);
+            }
+            if (ci + 1 == n_chunks) CK(cudaEventRecord(E->ev[4], st));
             if (!out_dev) {
                 if (n_chunks > 1) {
                     CK(cudaEventRecord(E->evp[2], st));
                     CK(cudaStreamWaitEvent(cs, E->evp[2], 0));
                 }
-                CK(cudaMemcpyAsync(q->out_ids + r0 * k_out, o_ids + r0 * k_out, sizeof(int32_t) * (r1 - r0) * k_out, cudaMemcpyDeviceToHost, cs));
-                CK(cudaMemcpyAsync(q->out_scores + r0 * k_out, o_scores + r0 * k_out, sizeof(float) * (r1 - r0) * k_out, cudaMemcpyDeviceToHost, cs));
-                CK(cudaMemcpyAsync(q->out_counts + r0, o_counts + r0, sizeof(int32_t) * (r1 - r0), cudaMemcpyDeviceToHost, cs));
-                S.d2h_bytes += (int64_t)((r1 - r0) * k_out * 8 + (r1 - r0) * 4);
+                copy_back(r0, r1, cs);
+            }
+        }
+        // ---------------- rows whose certificate failed in the main pass (all chunks): re-rank, patch the results
+        int64_t n_fb = 0;
+        if (use_tc && !multipass_main && !peers && !sparse_sub) {
+            n_fb = read_counter(c, cnt);
+            S.n_fallback_rows = n_fb;
+            if (n_fb > 0) {
+                rerank_rows(fb1, n_fb);
+                if (E->id_offset != 0) {
+                    add_offset_rows_kernel<<<grid_for(n_fb * k_out, 256), 256, 0, st>>>(c.o_ids, fb1, n_fb, k_out, (int32_t)E->id_offset);
+                    CK(cudaGetLastError());
+                    S.n_launches++;
+                }
+                if (!out_dev) {
+                    // packed copies of the patched rows: one more small transfer, scattered into the caller's arrays below
+                    const size_t row_bytes = (size_t)k_out * 8 + 8;
+                    E->patch.ensure(row_bytes * n_fb);
+                    int32_t* g_ids = E->patch.as<int32_t>();
+                    float* g_sc = reinterpret_cast<float*>(g_ids + n_fb * k_out);
+                    int32_t* g_cnt = reinterpret_cast<int32_t*>(g_sc + n_fb * k_out);
+                    int32_t* g_rows = g_cnt + n_fb;
+                    gather_rows_kernel<<<grid_for(n_fb * k_out, 256), 256, 0, st>>>(c.o_ids, c.o_scores, c.o_counts, fb1, n_fb, k_out, g_ids,
+                                                                                   g_sc, g_cnt);
+                    CK(cudaGetLastError());
+                    CK(cudaMemcpyAsync(g_rows, fb1, sizeof(int32_t) * n_fb, cudaMemcpyDeviceToDevice, st));
+                    E->h_patch.resize(row_bytes * n_fb);
+                    if (n_chunks > 1) {  // the caller's arrays must hold the chunk copies before they are patched
+                        CK(cudaEventRecord(E->evp[2], cs));
+                        CK(cudaStreamWaitEvent(st, E->evp[2], 0));
+                    }
+                    CK(cudaMemcpyAsync(E->h_patch.data(), E->patch.p, row_bytes * n_fb, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    const int32_t* h_ids = reinterpret_cast<const int32_t*>(E->h_patch.data());
+                    const float* h_sc = reinterpret_cast<const float*>(h_ids + n_fb * k_out);
+                    const int32_t* h_cnt = reinterpret_cast<const int32_t*>(h_sc + n_fb * k_out);
+                    const int32_t* h_rows = h_cnt + n_fb;
+                    for (int64_t i = 0; i < n_fb; ++i) {
+                        const int64_t r = h_rows[i];
+                        memcpy(q->out_ids + r * k_out, h_ids + i * k_out, sizeof(int32_t) * k_out);
+                        memcpy(q->out_scores + r * k_out, h_sc + i * k_out, sizeof(float) * k_out);
+                        q->out_counts[r] = h_cnt[i];
+                    }
+                    S.d2h_bytes += (int64_t)(row_bytes * n_fb);
+                }
             }
         }
         if (n_chunks > 1) {  // the main stream (and through it the caller) sees the copies of the last chunks
@@ -1048,19 +1286,23 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         CK(cudaStreamSynchronize(st));
         CK(cudaEventElapsedTime(&S.ms_total, E->ev[0], E->ev[5]));
         CK(cudaEventElapsedTime(&S.ms_h2d, E->ev[0], E->ev[1]));  // exposed part: the first chunk's inputs
-        CK(cudaEventElapsedTime(&S.ms_d2h, E->ev[4], E->ev[5]));  // exposed part: the last chunk's results
+        CK(cudaEventElapsedTime(&S.ms_d2h, E->ev[4], E->ev[5]));  // exposed part: the last chunk's results (+ re-ranked rows)
+        c.collect_times();
     } catch (const CudaError& ce) {
         return fail(ce.e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "b200_rank_topk: %s failed at line %d: %s", ce.what,
                     ce.line, cudaGetErrorString(ce.e));
     }
-    if (stats) *stats = S;
+    if (stats) *stats = c.S;
     return B200_OK;
 }
 
-int b200_rank_merge(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids,
-                    const float* scores, const int32_t* counts, int32_t* out_ids, float* out_scores, int32_t* out_counts) {
+static int merge_impl(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids, const float* scores,
+                      const int32_t* counts, const float* bounds, int64_t list_stride, int32_t* out_ids, float* out_scores,
+                      int32_t* out_counts, int32_t* fail_rows, int32_t* fail_count) {
     if (n_lists <= 0 || n_rows < 0 || k <= 0 || !ids || !scores || !counts || !out_ids || !out_scores || !out_counts)
         return fail(B200_E_INVALID, "b200_rank_merge: bad arguments");
+    if (bounds && (!fail_rows || !fail_count)) return fail(B200_E_INVALID, "b200_rank_merge_certified: fail_rows / fail_count are NULL");
+    if (bounds && k > 32) return fail(B200_E_UNSUPPORTED, "b200_rank_merge_certified: k <= 32");
     if (n_rows == 0) return B200_OK;
     try {
         CK(cudaSetDevice(device));
@@ -1072,23 +1314,40 @@ int b200_rank_merge(int32_t device, void* stream, int32_t n_lists, int64_t n_row
             sp.in_scores = scores;
             sp.in_ids = ids;
             sp.in_counts = counts;
+            sp.in_bounds = bounds;
             sp.n_lists = n_lists;
             sp.L = k;
             sp.n_sel = n_rows;
             sp.list_stride_rows = n_rows;
+            sp.list_stride_elems = list_stride;
             sp.k_out = k;
             sp.k0 = k0;
             sp.kp = std::min(32, k - k0);
             sp.out_ids = out_ids;
             sp.out_scores = out_scores;
             sp.out_counts = out_counts;
-            select_kernel<false><<<grid_for(n_rows, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
+            sp.fb_rows = fail_rows;
+            sp.fb_count = fail_count;
+            merge_select_kernel<<<grid_for(n_rows, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(sp);
             CK(cudaGetLastError());
         }
     } catch (const CudaError& ce) {
         return fail(B200_E_CUDA, "b200_rank_merge: %s failed: %s", ce.what, cudaGetErrorString(ce.e));
     }
     return B200_OK;
+}
+
+int b200_rank_merge(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids,
+                    const float* scores, const int32_t* counts, int32_t* out_ids, float* out_scores, int32_t* out_counts) {
+    return merge_impl(device, stream, n_lists, n_rows, k, ids, scores, counts, nullptr, 0, out_ids, out_scores, out_counts, nullptr, nullptr);
+}
+
+int b200_rank_merge_certified(int32_t device, void* stream, int32_t n_lists, int64_t n_rows, int32_t k, const int32_t* ids,
+                              const float* scores, const int32_t* counts, const float* bounds, int64_t list_stride, int32_t* out_ids,
+                              float* out_scores, int32_t* out_counts, int32_t* fail_rows, int32_t* fail_count) {
+    if (!bounds) return fail(B200_E_INVALID, "b200_rank_merge_certified: bounds is NULL");
+    return merge_impl(device, stream, n_lists, n_rows, k, ids, scores, counts, bounds, list_stride, out_ids, out_scores, out_counts,
+                      fail_rows, fail_count);
 }
 
 }  // extern "C"

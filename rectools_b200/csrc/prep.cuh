@@ -109,4 +109,39 @@ __global__ void gather_rows16_kernel(const uint4* __restrict__ in, const int32_t
     out[i] = v;
 }
 
+// fp16 / bf16 factors handed over as device tensors -> fp32 (exact widening).
+__global__ void widen16_kernel(const void* __restrict__ in, int is_bf16, int64_t n, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[i]) : __half2float(reinterpret_cast<const __half*>(in)[i]);
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ out, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)i;
+}
+
+// [n, d] row-major -> [d, n] row-major (32 x 32 tiles through shared memory).
+__global__ void transpose_kernel(const float* __restrict__ in, int64_t n, int d, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i;
+        const int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < n && c < d) ? in[r * d + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i;
+        const int64_t r = r0 + threadIdx.x;
+        if (c < d && r < n) out[(int64_t)c * n + r] = tile[threadIdx.x][i];
+    }
+}
+
 }  // namespace b200

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import typing as tp
+import weakref
 from enum import Enum
 
 import numpy as np
@@ -39,8 +40,8 @@ def _as_distance(distance: tp.Any) -> Distance:
 def _dense_f32(x: tp.Any) -> np.ndarray:
     """`factors.astype(np.float32)` of the reference (rank_implicit.py:70-71), C-contiguous, torch tensors accepted."""
     if sparse.issparse(x):
-        x = x.toarray()  # the reference GPU path densifies too (rank_implicit.py:157-159)
-    elif hasattr(x, "detach") and hasattr(x, "cpu"):
+        raise TypeError("sparse factors are kept sparse (B200Ranker: CSR subjects), never densified as a whole")
+    if hasattr(x, "detach") and hasattr(x, "cpu"):
         x = x.detach().cpu().numpy()
     x = np.asarray(x)
     if x.ndim != 2:
@@ -57,6 +58,17 @@ def _norms_f32(x: np.ndarray) -> np.ndarray:
     n = np.sqrt(np.einsum("ij,ij->i", x, x, dtype=np.float64)).astype(np.float32)
     n[n == 0] = 1e-10
     return n
+
+
+def check_whitelist(whitelist: np.ndarray, n_objects: int) -> None:
+    """`sorted_object_whitelist` (rank.py:39): object ids in range, strictly ascending -- the kernels merge a row's viewed ids
+    against the whitelist positions in ascending order, so an unsorted whitelist would let viewed objects through."""
+    if len(whitelist) == 0:
+        return
+    if whitelist[0] < 0 or whitelist[-1] >= n_objects or whitelist.min() < 0 or whitelist.max() >= n_objects:
+        raise IndexError("whitelist id out of range")
+    if len(whitelist) > 1 and not bool((np.diff(whitelist) > 0).all()):
+        raise ValueError("`sorted_object_whitelist` must be sorted ascending without duplicates")
 
 
 def prepare_factors(
@@ -86,6 +98,7 @@ class Engine:
         id_offset: int = 0,
         objects_device_ptr: tp.Optional[int] = None,
         shape: tp.Optional[tp.Tuple[int, int]] = None,
+        objects_dtype: int = _lib.DT_F32,
     ) -> None:
         self._lib = _lib.load()
         self._h = C.c_void_p()
@@ -100,8 +113,9 @@ class Engine:
             ptr, flags = objects.ctypes.data, 0
             self._keep = objects
         _lib.check(
-            self._lib.b200_rank_create(
-                C.byref(self._h), ptr, n, d, _lib.DIST_COSINE if cosine else _lib.DIST_DOT, device, _TC_MODES[tc_mode], flags
+            self._lib.b200_rank_create_ex(
+                C.byref(self._h), ptr, objects_dtype, n, d, _lib.DIST_COSINE if cosine else _lib.DIST_DOT, device,
+                _TC_MODES[tc_mode], flags,
             )
         )
         self._keep = None  # the engine copied the host matrix
@@ -136,14 +150,34 @@ class Engine:
         subjects = np.ascontiguousarray(subjects, dtype=np.float32)
         if subjects.shape[1] != self.d:
             raise ValueError("subject and object factors must have the same number of columns")
-        self.subjects_owner = owner
+        self._subjects_owner = weakref.ref(owner) if owner is not None else None
         if key is not None and key == getattr(self, "_subjects_key", None):
             return
         _lib.check(self._lib.b200_rank_set_subjects(self._h, subjects.ctypes.data, subjects.shape[0], 0))
         self._subjects_key = key
 
+    @property
+    def subjects_owner(self) -> tp.Any:
+        """The ranker whose subject factors are resident (None: nobody's / collected).  A weak reference: a cached engine
+        must not keep its last ranker and that ranker's matrices alive."""
+        ref = getattr(self, "_subjects_owner", None)
+        return ref() if ref is not None else None
+
     def set_subjects_device(self, ptr: int, n_subjects: int) -> None:
         _lib.check(self._lib.b200_rank_set_subjects(self._h, ptr, n_subjects, 1))
+
+    def peer_export(self, max_rows: int) -> bytes:
+        """Allocate this engine's published-threshold array (threshold sharing between the ranks of an item-sharded
+        catalogue) and return its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self._lib.b200_rank_peer_export(self._h, int(max_rows), buf))
+        return buf.raw
+
+    def peer_import(self, handles: tp.Sequence[bytes], self_index: int) -> None:
+        """Open the published-threshold arrays of all ranks (`handles` in rank order, this engine's own included)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        _lib.check(self._lib.b200_rank_peer_import(self._h, len(handles), int(self_index), blob))
 
     def topk_raw(self, q: _lib.Query) -> tp.Dict[str, tp.Any]:
         st = _lib.Stats()
@@ -167,9 +201,13 @@ class Engine:
         whitelist: int = 0,
         n_whitelist: int = 0,
         stream: int = 0,
+        out_bounds: int = 0,
+        peer_epoch: int = 0,
+        subject_dtype: int = _lib.DT_F32,
     ) -> tp.Dict[str, tp.Any]:
         """Raw-pointer call (host or device addresses according to `flags`); returns the call statistics."""
         q = _lib.Query()
+        q.out_bounds, q.peer_epoch, q.subject_dtype = out_bounds or None, int(peer_epoch), int(subject_dtype)
         q.subjects, q.subject_ids, q.n_rows, q.n_subjects_total = subjects or None, subject_ids or None, n_rows, n_subjects_total
         q.csr_indptr, q.csr_indices = indptr or None, indices or None
         q.whitelist, q.n_whitelist = whitelist or None, n_whitelist
@@ -188,10 +226,22 @@ class Engine:
         whitelist: tp.Optional[np.ndarray] = None,
         flags: int = 0,
         out: tp.Optional[tp.Tuple[np.ndarray, np.ndarray, np.ndarray]] = None,
+        sparse_subjects: tp.Optional[sparse.csr_matrix] = None,
     ) -> tp.Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """Host-buffer call: returns padded `(ids [n,k_out] int32, scores [n,k_out] fp32, counts [n] int32)`."""
+        """Host-buffer call: returns padded `(ids [n,k_out] int32, scores [n,k_out] fp32, counts [n] int32)`.
+        `sparse_subjects`: the batch rows as a CSR matrix [n_rows, d] (EASE), instead of `subjects` / `subject_ids`."""
         q = _lib.Query()
         keep = []
+        if sparse_subjects is not None:
+            if subjects is not None or subject_ids is not None:
+                raise ValueError("sparse_subjects excludes subjects / subject_ids")
+            if sparse_subjects.shape[1] != self.d:
+                raise ValueError("subject and object factors must have the same number of columns")
+            sp_indptr = np.ascontiguousarray(sparse_subjects.indptr, dtype=np.int64)
+            sp_indices = np.ascontiguousarray(sparse_subjects.indices, dtype=np.int32)
+            sp_data = np.ascontiguousarray(sparse_subjects.data, dtype=np.float32)
+            q.sub_indptr, q.sub_indices, q.sub_data = sp_indptr.ctypes.data, sp_indices.ctypes.data, sp_data.ctypes.data
+            keep += [sp_indptr, sp_indices, sp_data]
         if subjects is not None:
             subjects = np.ascontiguousarray(subjects, dtype=np.float32)
             if subjects.ndim != 2 or subjects.shape[1] != self.d:
@@ -204,6 +254,8 @@ class Engine:
             keep.append(subject_ids)
             n_rows = len(subject_ids)
             q.n_subjects_total = 0 if subjects is None else subjects.shape[0]
+        elif sparse_subjects is not None:
+            n_rows = sparse_subjects.shape[0]
         else:
             if subjects is None:
                 raise ValueError("either subjects or subject_ids is required")
@@ -280,6 +332,7 @@ class B200Ranker:
         subjects_key: tp.Optional[tp.Hashable] = None,
     ) -> None:
         self.distance = _as_distance(distance)
+        self._subjects_csr = None
         if sparse.issparse(subjects_factors) and self.distance != Distance.DOT:
             raise ValueError("To use `sparse.csr_matrix` distance must be `Distance.DOT`")  # rank_implicit.py:66-67
         if engine is None and self.distance != Distance.EUCLIDEAN and _is_cuda_tensor(objects_factors):
@@ -287,8 +340,22 @@ class B200Ranker:
             # rectools/models/nn/transformers/lightning.py:391, :398): hand the device pointers over, no host round trip
             self._init_from_device_tensors(subjects_factors, objects_factors, tc_mode)
             return
-        subjects = _dense_f32(subjects_factors)
         objects = _dense_f32(objects_factors)
+        if sparse.issparse(subjects_factors):
+            # EASE: the subjects are the user x item interaction CSR (rectools/models/ease.py:134-161).  The reference keeps the
+            # matrix sparse and densifies only the requested rows (rank_implicit.py:236, :157-160); here the rows stay sparse
+            # all the way into the SpMM scorer of the engine.
+            csr = subjects_factors.tocsr()
+            if csr.shape[1] != objects.shape[1]:
+                raise ValueError("subject and object factors must have the same number of columns")
+            self._subjects_csr = csr.astype(np.float32)
+            self.n_subjects, self.n_objects = csr.shape[0], objects.shape[0]
+            self.subjects_norms = self.subjects_dots = None
+            self.engine = engine or Engine(objects, cosine=False, device=device, tc_mode=tc_mode)
+            self._subjects, self._subjects_key = None, None
+            self.last_stats = {}
+            return
+        subjects = _dense_f32(subjects_factors)
         if subjects.shape[1] != objects.shape[1]:
             raise ValueError("subject and object factors must have the same number of columns")
         self.n_subjects, self.n_objects = subjects.shape[0], objects.shape[0]
@@ -301,9 +368,16 @@ class B200Ranker:
     def _init_from_device_tensors(self, subjects_factors: tp.Any, objects_factors: tp.Any, tc_mode: str) -> None:
         import torch
 
-        objects = objects_factors.detach().to(torch.float32).contiguous()
+        # fp16 / bf16 embeddings go to the engine as they are (widened exactly on the device: b200_rank_create_ex)
+        dtypes = {torch.float32: _lib.DT_F32, torch.float16: _lib.DT_F16, torch.bfloat16: _lib.DT_BF16}
+        objects = objects_factors.detach()
+        if objects.dtype not in dtypes:
+            objects = objects.to(torch.float32)
+        objects = objects.contiguous()
         dev = objects.device
         subjects = subjects_factors
+        if sparse.issparse(subjects):
+            raise ValueError("CSR subjects need host object factors")
         if not hasattr(subjects, "detach"):
             subjects = torch.from_numpy(_dense_f32(subjects))
         subjects = subjects.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -319,9 +393,10 @@ class B200Ranker:
         self._device_tensors = (subjects, objects)  # the engine references this memory: keep it alive
         self.engine = Engine(
             None, cosine=self.distance == Distance.COSINE, device=dev.index or 0, tc_mode=tc_mode,
-            objects_device_ptr=objects.data_ptr(), shape=(self.n_objects, int(objects.shape[1])),
+            objects_device_ptr=objects.data_ptr(), shape=(self.n_objects, int(objects.shape[1])), objects_dtype=dtypes[objects.dtype],
         )
         self.engine.set_subjects_device(subjects.data_ptr(), self.n_subjects)
+        self._subjects = self._subjects_key = None
         self.last_stats = {}
 
     # ------------------------------------------------------------------------------------------------------------
@@ -343,8 +418,7 @@ class B200Ranker:
         n_pos = self.n_objects
         if sorted_object_whitelist is not None:
             whitelist = np.asarray(sorted_object_whitelist, dtype=np.int64).reshape(-1)
-            if len(whitelist) and (whitelist.min() < 0 or whitelist.max() >= self.n_objects):
-                raise IndexError("whitelist id out of range")
+            check_whitelist(whitelist, self.n_objects)
             n_pos = len(whitelist)
         if k is None:
             k = n_pos  # rank_implicit.py:233-234
@@ -359,7 +433,14 @@ class B200Ranker:
         if n_pos == 0 or len(subject_ids) == 0:
             z = np.empty((len(subject_ids), 0))
             return subject_ids, z.astype(np.int32), z.astype(np.float32), np.zeros(len(subject_ids), np.int32)
-        if getattr(self, "_subjects", None) is not None and getattr(self.engine, "subjects_owner", self) is not self:
+        if self._subjects_csr is not None:
+            rows = self._subjects_csr[subject_ids]  # CSR row gather: cheap, stays sparse (rank_implicit.py:236)
+            ids, scores, counts = self.engine.topk(
+                k, sparse_subjects=rows, indptr=indptr, indices=indices, whitelist=whitelist, flags=flags & ~_lib.Q_FORCE_TC
+            )
+            self.last_stats = self.engine.last_stats
+            return subject_ids, ids, scores, counts
+        if getattr(self, "_subjects", None) is not None and self.engine.subjects_owner is not self:
             # another ranker sharing this (cached) engine made its own subject factors resident in the meantime
             self.engine.set_subjects(self._subjects, key=self._subjects_key, owner=self)
         ids, scores, counts = self.engine.topk(

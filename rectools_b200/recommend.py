@@ -26,7 +26,7 @@ from .ranker import Distance, _as_distance
 USER_COL, ITEM_COL, SCORE_COL, RANK_COL = "user_id", "item_id", "score", "rank"  # rectools/columns.py:21-27
 TARGET_ITEM_COL = "target_item_id"  # rectools/columns.py:23
 
-_CSR_CACHE: "tp.Dict[int, tp.Tuple[tp.Any, tp.Any]]" = {}
+_CSR_CACHE: "tp.Dict[int, tp.Tuple[tp.Any, tp.Any, tp.Any]]" = {}
 
 
 def viewed_csr(dataset: tp.Any) -> tp.Any:
@@ -34,10 +34,15 @@ def viewed_csr(dataset: tp.Any) -> tp.Any:
 
     The reference rebuilds this CSR from the interactions DataFrame on every `recommend()` call; it only depends on that
     (immutable by convention) table, so it is cached by the table's identity and dropped when the table is collected."""
+    from .integration import content_hash
+
     df = dataset.interactions.df
     key = id(df)
+    # the CSR structure depends on the (user, item) columns only: their content digest catches in-place edits of the table
+    stamp = (len(df), content_hash(np.asarray(df[USER_COL].values)), content_hash(np.asarray(df[ITEM_COL].values)),
+             dataset.user_id_map.size, dataset.item_id_map.size)
     hit = _CSR_CACHE.get(key)
-    if hit is not None and hit[0]() is df:
+    if hit is not None and hit[0]() is df and hit[2] == stamp:
         return hit[1]
     csr = dataset.get_user_item_matrix(include_weights=False)
     if not csr.has_sorted_indices:
@@ -46,7 +51,7 @@ def viewed_csr(dataset: tp.Any) -> tp.Any:
         ref = weakref.ref(df, lambda _r, key=key: _CSR_CACHE.pop(key, None))
     except TypeError:  # not weak-referenceable: do not cache
         return csr
-    _CSR_CACHE[key] = (ref, csr)
+    _CSR_CACHE[key] = (ref, csr, stamp)
     return csr
 
 
@@ -140,9 +145,10 @@ def recommend(  # pylint: disable=too-many-locals
     whitelist = model._get_sorted_item_ids_to_recommend(items_to_recommend, ds)  # pylint: disable=protected-access
     hot, warm, cold = model._split_targets_by_hot_warm_cold(users, ds, "user")  # pylint: disable=protected-access
     hot, warm, cold = model._check_targets_are_valid(hot, warm, cold, "user", on_unsupported_targets)  # pylint: disable=protected-access
-    if np.size(warm) > 0 or np.size(cold) > 0:
-        return delegate()
     hot = np.asarray(hot, dtype=np.int64)
+    if np.size(warm) > 0 or np.size(cold) > 0 or len(np.unique(hot)) != len(hot):
+        # (repeated targets: the reference's rank column runs across the repeats, `groupby(user).cumcount()`, base.py:778-791)
+        return delegate()
 
     csr = _rows_of(viewed_csr(ds), hot) if (filter_viewed and hot.size) else None
     user_vectors, item_vectors = model._get_u2i_vectors(ds)  # pylint: disable=protected-access

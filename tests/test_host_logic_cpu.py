@@ -13,7 +13,7 @@ class RecordingLib:
     def __init__(self):
         self.calls = []
 
-    def b200_rank_create(self, out, ptr, n, d, dist, device, tc, flags):
+    def b200_rank_create_ex(self, out, ptr, dtype, n, d, dist, device, tc, flags):
         out._obj.value = 1 + len([c for c in self.calls if c[0] == "create"])  # pylint: disable=protected-access
         self.calls.append(("create", int(n), int(d), int(dist)))
         return 0
@@ -91,3 +91,31 @@ def test_shared_cached_engine_keeps_the_right_subjects_resident(lib):
     # COSINE needs its own engine (pre-normalised object copy)
     B200ImplicitRanker("cosine", users_a, items)
     assert [c for c in lib.calls if c[0] == "create"][-1][3] == 1 and len([c for c in lib.calls if c[0] == "create"]) == 2
+
+
+def test_in_place_refit_is_detected(lib):
+    """The engine / subject caches are keyed by the CONTENT of the factor matrices: an in-place change of a single element
+    (a refit that reuses the arrays) must reach the device, an unchanged matrix must not be uploaded again."""
+    from rectools_b200 import B200ImplicitRanker
+    from rectools_b200.integration import content_hash
+
+    items = np.random.default_rng(0).random((5000, 64), dtype=np.float32)
+    users = np.random.default_rng(1).random((300, 64), dtype=np.float32)
+    B200ImplicitRanker("dot", users, items)
+    B200ImplicitRanker("dot", users, items)
+    assert [c[0] for c in lib.calls] == ["create", "set_subjects"]
+    items[4321, 17] += 1e-3  # not on any sampling stride
+    B200ImplicitRanker("dot", users, items)
+    assert [c[0] for c in lib.calls].count("create") == 2
+    users[299, 63] = 0.5
+    B200ImplicitRanker("dot", users, items)
+    assert [c[0] for c in lib.calls].count("create") == 2 and [c[0] for c in lib.calls].count("set_subjects") == 3
+    # position sensitive (two rows swapped), shape sensitive, tail bytes covered
+    a = np.arange(3 * 100003, dtype=np.float32).reshape(3, 100003)
+    b = a.copy()
+    b[[0, 1]] = b[[1, 0]]
+    assert content_hash(a) != content_hash(b) and content_hash(a) == content_hash(a.copy())
+    assert content_hash(a) != content_hash(a.reshape(100003, 3))
+    c = a.copy()
+    c[-1, -1] += 1
+    assert content_hash(a) != content_hash(c)
