@@ -46,6 +46,23 @@ def num_threads() -> int:
     return int(_lib().ref_num_threads())
 
 
+def use_all_threads() -> int:
+    """Give BLAS (numpy's sgemm) and the OpenMP select every core this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its workers: the round-1 reference arm silently ran on one thread at N > 1).
+    Returns the thread count; pass it to `topk_cpu(num_threads=...)`."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=n)  # process-wide, stays in force
+    except Exception:  # pylint: disable=broad-except
+        pass
+    return n
+
+
 def topk_cpu(
     items: np.ndarray,
     query: np.ndarray,

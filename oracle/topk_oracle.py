@@ -70,8 +70,8 @@ def _select_topk_rows(scores: np.ndarray, k: int) -> tp.Tuple[np.ndarray, np.nda
 
 
 def _score_block(query: np.ndarray, items: np.ndarray, item_norms: tp.Optional[np.ndarray], accum: str) -> np.ndarray:
-    if accum == "f64":
-        s = query.astype(np.float64) @ items.astype(np.float64).T
+    if accum == "f64":  # (`items` arrives already widened: implicit_topk converts the catalogue once, not per batch)
+        s = query.astype(np.float64) @ items.T
         if item_norms is not None:
             s = s / item_norms.astype(np.float64)[None, :]
         return s.astype(np.float32)
@@ -110,9 +110,10 @@ def implicit_topk(
         indptr, indices = filter_query_items.indptr, filter_query_items.indices
     ids = np.empty((n_q, k), dtype=np.int32)
     scores = np.empty((n_q, k), dtype=np.float32)
+    items_acc = items.astype(np.float64) if accum == "f64" else items
     for start in range(0, n_q, batch):
         stop = min(start + batch, n_q)
-        s = _score_block(query[start:stop], items, item_norms, accum)
+        s = _score_block(query[start:stop], items_acc, item_norms, accum)
         if filter_query_items is not None:
             for r in range(start, stop):
                 cols = indices[indptr[r] : indptr[r + 1]]
@@ -133,8 +134,10 @@ def rank_oracle(  # pylint: disable=too-many-locals,too-many-branches
     filter_pairs_csr: tp.Optional[sparse.csr_matrix] = None,
     sorted_object_whitelist: tp.Optional[np.ndarray] = None,
     accum: str = "f32",
+    batch: int = 512,
 ) -> tp.Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Restatement of ``ImplicitRanker(distance, S, O).rank(...)``.
+    """Restatement of ``ImplicitRanker(distance, S, O).rank(...)``.  ``batch``: subjects per score block (memory bound of
+    the restatement, no effect on the result).
 
     Steps follow rank_implicit.py: fp32 casts (:70-71), shape check (:215-217),
     whitelist gather and CSR column restriction (:219-226), subject gather
@@ -187,7 +190,7 @@ def rank_oracle(  # pylint: disable=too-many-locals,too-many-branches
         raise ValueError(f"Unexpected distance `{distance}`")
 
     real_k = min(int(k), objects.shape[0])
-    ids, scores = implicit_topk(objects, subjects, real_k, norms, filt, None, accum=accum)
+    ids, scores = implicit_topk(objects, subjects, real_k, norms, filt, None, accum=accum, batch=batch)
     if wl is not None:
         ids = wl[ids]
 

@@ -882,7 +882,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         if (stats) *stats = S;
         return B200_OK;
     }
-    if (shared && n_rows > E->peer_rows)
+    if (shared && E->n_peers > 0 && n_rows > E->peer_rows)
         return fail(B200_E_INVALID, "b200_rank_topk: %lld rows exceed the %lld exported for threshold sharing", (long long)n_rows,
                     (long long)E->peer_rows);
     try {

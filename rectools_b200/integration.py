@@ -202,13 +202,19 @@ def uninstall() -> None:
     clear_engine_cache()
 
 
-def make_similarity_module() -> type:
-    """`similarity_module_type` for SASRec / BERT4Rec / HSTU: same module, `B200TorchRanker` as the scorer."""
-    from rectools.models.nn.transformers.similarity import DistanceSimilarityModule  # needs torch + lightning
+def make_similarity_module(ranker_factory: tp.Optional[tp.Callable[..., tp.Any]] = None) -> type:
+    """`similarity_module_type` for SASRec / BERT4Rec / HSTU (rectools/models/nn/transformers/base.py:219, :423): the
+    reference's `DistanceSimilarityModule` with `B200TorchRanker` as the scorer of `_recommend_u2i`
+    (similarity.py:117-140).  `item_embs` stays on its device (and in its dtype: fp16 / bf16 embeddings are handed to the
+    engine as they are); the filter stays a CSR (the reference densifies [batch, n_items] per batch, rank_torch.py:138-144).
+    `ranker_factory`: another `TorchRanker`-signature class (the CPU tests plug an oracle-backed stand-in in)."""
+    from rectools.models.nn.transformers.similarity import DistanceSimilarityModule  # needs torch only
+
+    factory = ranker_factory or B200TorchRanker
 
     class B200DistanceSimilarityModule(DistanceSimilarityModule):
         def _recommend_u2i(self, user_embs, item_embs, user_ids, k, sorted_item_ids_to_recommend, ui_csr_for_filter):
-            ranker = B200TorchRanker(
+            ranker = factory(
                 distance=self.distance, device=item_embs.device, subjects_factors=user_embs[user_ids],
                 objects_factors=item_embs,
             )
@@ -219,4 +225,3 @@ def make_similarity_module() -> type:
             return user_ids[user_ids_indices], all_reco_ids, all_scores
 
     return B200DistanceSimilarityModule
-

@@ -374,50 +374,65 @@ class ShardedB200Ranker:
         return (subject_ids,) + tuple(self._collect(*o, row_bounds, k))
 
     def rank_device(self, subjects: tp.Any, k: int, indptr: tp.Any = None, indices: tp.Any = None):
-        """Device inputs, device outputs: `subjects` [n, d] fp32 CUDA tensor = THIS subject group's rows of the batch in batch
-        order (all rows with pure item sharding), `indptr` int64 [n+1] / `indices` int32 CUDA tensors = their filter rows.
-        Returns `(ids [n_all,k], scores, counts)` CUDA tensors of the whole batch.  DOT / COSINE scores as the engine defines
-        them (COSINE: not yet divided by the subject norms)."""
+        """Subject MATRIX in, device tensors out: `subjects` [n, d] fp32 = THIS subject group's rows of the batch in batch order
+        (all rows with pure item sharding), `indptr` int64 [n+1] / `indices` int32 = their filter rows -- either CUDA tensors
+        (resident inputs, no copies) or host arrays / pinned CPU tensors (staged by the engine's chunk pipeline: the copies
+        overlap the ranking).  Returns `(ids [n_all,k], scores, counts)` CUDA tensors of the whole batch.  DOT / COSINE scores
+        as the engine defines them (COSINE: not yet divided by the subject norms)."""
         from . import _lib
 
         torch = self.torch
+        on_device = bool(getattr(subjects, "is_cuda", False))
+        if not on_device:  # host: numpy views (pinned tensors stay pinned)
+            to_np = lambda t, dt: None if t is None else np.ascontiguousarray(t.numpy() if hasattr(t, "numpy") else t, dtype=dt)
+            subjects, indptr, indices = to_np(subjects, np.float32), to_np(indptr, np.int64), to_np(indices, np.int32)
+        ptr = (lambda t: t.data_ptr()) if on_device else (lambda t: t.ctypes.data)
         n = int(subjects.shape[0])
-        n_all = n if self.subject_groups == 1 else None
-        if n_all is None:  # the groups' slice lengths
-            t = torch.tensor([n], dtype=torch.int64, device=subjects.device)
+        if self.subject_groups > 1:  # the groups' slice lengths
+            t = torch.tensor([n], dtype=torch.int64, device=self.local.device)
             sizes = [torch.zeros_like(t) for _ in range(self.subject_groups)]
             self.dist.all_gather(sizes, t, group=self.collect_group)
-            lens = [int(x.item()) for x in sizes]
-            starts = np.concatenate([[0], np.cumsum(lens)])
+            starts = np.concatenate([[0], np.cumsum([int(x.item()) for x in sizes])])
             row_bounds = [(int(starts[i]), int(starts[i + 1])) for i in range(self.subject_groups)]
         else:
             row_bounds = [(0, n)]
         k = min(int(k), self.n_objects)
 
-        def dev_inputs(sub_t, ip_t, ix_t):
-            kw = dict(subjects=sub_t.data_ptr(), flags=_lib.Q_INPUTS_ON_DEVICE)
+        def inputs(sub_t, ip_t, ix_t):
+            kw = dict(subjects=ptr(sub_t), flags=_lib.Q_INPUTS_ON_DEVICE if on_device else 0)
             if ip_t is not None:
-                kw.update(indptr=ip_t.data_ptr(), indices=ix_t.data_ptr())
+                kw.update(indptr=ptr(ip_t), indices=ptr(ix_t))
             return kw
 
         shared = self._shared_ok(n, k)
         pk = Packed(torch, n, k, self.local.device)
         self.last_stats = dict(self.local.local_topk(n, k, pk, shared_epoch=self._next_epoch() if shared else 0,
-                                                     **dev_inputs(subjects, indptr, indices)))
+                                                     **inputs(subjects, indptr, indices)))
 
         def rerank(rows):
-            sub2 = subjects[rows].contiguous()
-            ip2 = ix2 = None
-            if indptr is not None:
-                a, b = indptr[rows], indptr[rows + 1]
-                lens = b - a
-                ip2 = torch.zeros((len(rows) + 1,), dtype=torch.int64, device=indptr.device)
-                ip2[1:] = torch.cumsum(lens, 0)
-                pos = torch.arange(int(ip2[-1].item()), device=indptr.device) - torch.repeat_interleave(ip2[:-1], lens) + torch.repeat_interleave(a, lens)
-                ix2 = indices[pos].contiguous()
+            if on_device:
+                sub2 = subjects[rows].contiguous()
+                ip2 = ix2 = None
+                if indptr is not None:
+                    a, b = indptr[rows], indptr[rows + 1]
+                    lens = b - a
+                    ip2 = torch.zeros((len(rows) + 1,), dtype=torch.int64, device=indptr.device)
+                    ip2[1:] = torch.cumsum(lens, 0)
+                    pos = (torch.arange(int(ip2[-1].item()), device=indptr.device) - torch.repeat_interleave(ip2[:-1], lens)
+                           + torch.repeat_interleave(a, lens))
+                    ix2 = indices[pos].contiguous()
+            else:
+                rows_np = rows.cpu().numpy()
+                sub2 = np.ascontiguousarray(subjects[rows_np])
+                ip2 = ix2 = None
+                if indptr is not None:
+                    lens = indptr[rows_np + 1] - indptr[rows_np]
+                    ip2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+                    ix2 = np.ascontiguousarray(np.concatenate([indices[indptr[r] : indptr[r + 1]] for r in rows_np]) if len(rows_np) else
+                                               np.empty(0, np.int32), dtype=np.int32)
             pk2 = Packed(torch, len(rows), k, self.local.device)
             self._keep = (sub2, ip2, ix2)
-            self.local.local_topk(len(rows), k, pk2, **dev_inputs(sub2, ip2, ix2))
+            self.local.local_topk(len(rows), k, pk2, **inputs(sub2, ip2, ix2))
             return pk2
 
         o = self._exchange(pk, n, k, shared, rerank)

@@ -1,8 +1,9 @@
-# round-2 starting point: the experimental 16-epilogue-warp kernel against the default
-bench gen3 ""
-bench gen4 "" B200_TC_KERNEL=4
-bench gen4_kc10 "" B200_TC_KERNEL=4 B200_TC_KCAND=10
-bench gen4_kc6 "" B200_TC_KERNEL=4 B200_TC_KCAND=6
-bench gen3_n125k "--items 125000"
-bench gen4_n125k "--items 125000" B200_TC_KERNEL=4
-bench gen4_1M "--users 1000000" B200_TC_KERNEL=4
+# A/B cases of scripts/gpu_ab.sh (sourced): label, extra bench args, environment
+bench epi8 ""
+bench epi16 "" B200_EPI_WARPS=16
+bench epi16_kc10 "" B200_EPI_WARPS=16 B200_TC_KCAND=10
+bench epi8_n125k "--items 125000"
+bench epi16_n125k "--items 125000" B200_EPI_WARPS=16
+bench c3_wide "--config c3 --users 151552"
+bench c3_wide16 "--config c3 --users 151552" B200_EPI_WARPS=16
+bench c3_multipass "--config c3 --users 75776" B200_WIDE=0

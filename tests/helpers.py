@@ -112,6 +112,24 @@ class OracleRanker:
         return subject_ids, ids, scores, counts
 
 
+class OracleTorchRanker:
+    """CPU stand-in with the `TorchRanker` constructor signature (rank_torch.py:59-67), backed by the oracle.  Keeps the torch
+    path's filter semantics: CSR VALUES != 0 filter (rank_torch.py:143).  Test infrastructure only."""
+
+    def __init__(self, distance, device, subjects_factors, objects_factors, batch_size=128, dtype=None):  # pylint: disable=unused-argument
+        self._dist = str(getattr(distance, "value", distance))
+        to_np = lambda t: t.detach().cpu().float().numpy() if hasattr(t, "detach") else np.asarray(t, dtype=np.float32)
+        self._u, self._i = to_np(subjects_factors), to_np(objects_factors)
+
+    def rank(self, subject_ids, k=None, filter_pairs_csr=None, sorted_object_whitelist=None):
+        from oracle.topk_oracle import rank_oracle
+
+        if filter_pairs_csr is not None:
+            filter_pairs_csr = filter_pairs_csr.copy()
+            filter_pairs_csr.eliminate_zeros()
+        return rank_oracle(self._dist, self._u, self._i, subject_ids, k, filter_pairs_csr, sorted_object_whitelist, accum="f64")
+
+
 class FakeIdMap:
     """The part of `rectools.dataset.IdMap` (identifiers.py:40-126) the vectorised recommend() touches."""
 

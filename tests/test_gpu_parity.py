@@ -183,12 +183,19 @@ def test_random_vs_oracle(rb, n_users, n_items, d, k, per_user, distance, tc_mod
             assert ranker.last_stats["n_fallback_rows"] <= max(4, n_users // 50), ranker.last_stats
 
 
-@pytest.mark.parametrize("distance, k, use_wl", [("dot", 100, False), ("cosine", 100, True), ("dot", 37, False)])
-def test_multi_pass_tensor_core_large_k(rb, distance, k, use_wl):
-    """k > 24 on the tensor-core path (BASELINE config 3 shape: COSINE, K = 100, ~100 viewed): passes of 20 results,
-    earlier results excluded like viewed objects; the concatenation must be the exact top-k in order."""
+@pytest.mark.parametrize("mode", ["wide", "multipass", "wide16"])
+@pytest.mark.parametrize("distance, k, use_wl", [("dot", 100, False), ("cosine", 100, True), ("dot", 37, False), ("cosine", 128, False)])
+def test_large_k_on_the_tensor_core_path(rb, monkeypatch, distance, k, use_wl, mode):
+    """24 < k <= 128 on the tensor-core path (BASELINE config 3 shape: COSINE, K = 100, ~100 viewed).
+    wide (default): ONE pass -- adaptive lists for the first part of the stream, then the frozen threshold + global append,
+    block-per-row re-score; rows whose certificate fails take the multi-pass route.  multipass (B200_WIDE=0): certified passes
+    of 20 results with the earlier results excluded like viewed objects.  Both must give the exact top-k in order."""
     from rectools_b200 import _lib
 
+    if mode == "multipass":
+        monkeypatch.setenv("B200_WIDE", "0")
+    if mode == "wide16":
+        monkeypatch.setenv("B200_EPI_WARPS", "16")
     n_users, n_items, d = 1500, 30_000, 64
     u, i = synth_factors(n_users, n_items, d, seed=k)
     csr = synth_viewed_csr(n_users, n_items, 100)
@@ -196,34 +203,45 @@ def test_multi_pass_tensor_core_large_k(rb, distance, k, use_wl):
     ranker = rb.B200Ranker(distance, u, i)
     sids = np.arange(n_users)
     _, ids, scores, counts = ranker.rank_padded(sids, k, csr, wl, flags=_lib.Q_FORCE_TC)
-    assert ranker.last_stats["path"] == 1 and (counts == k).all()
+    st = ranker.last_stats
+    assert st["path"] == 1 and (counts == k).all() and st["wide"] == (0 if mode == "multipass" else 1), st
+    if mode != "multipass":
+        assert st["n_tc_launches"] <= 1 + 12 * (st["n_fallback_rows"] > 0), st  # one main pass; re-rank passes only for failures
+        assert st["n_fallback_rows"] <= n_users // 10, st
     sel = sids[::5]
     _, oid, osc = rank_oracle(distance, u, i, sel, k, csr[sel], wl, accum="f64")
     if distance == "cosine":
         osc = osc * ranker.subjects_norms[np.repeat(sel, k)]
-    np.testing.assert_array_equal(ids[sel].reshape(-1), oid, err_msg=str(ranker.last_stats))
+    np.testing.assert_array_equal(ids[sel].reshape(-1), oid, err_msg=str(st))
     np.testing.assert_allclose(scores[sel].reshape(-1), osc, rtol=3e-7, atol=1e-9)
 
 
+def test_wide_mode_overflow_and_short_streams(rb, monkeypatch):
+    """Wide mode corner cases: a target far below what the catalogue offers (lists overflow -> rows re-ranked), duplicated
+    top objects (ties at the cut), a catalogue of a few tiles (phase 1 covers most of the stream)."""
+    from rectools_b200 import _lib
+
+    n_users, n_items, d, k = 700, 6_000, 32, 60
+    u, i = synth_factors(n_users, n_items, d, seed=3)
+    i[1000:1100] = i[1000]  # 100 identical objects
+    csr = synth_viewed_csr(n_users, n_items, 40)
+    ranker = rb.B200Ranker("dot", u, i)
+    sids = np.arange(n_users)
+    _, oid, osc = rank_oracle("dot", u, i, sids, k, csr, accum="f64")
+    for env in ({}, {"B200_WIDE_T": "400"}, {"B200_WIDE_T": "61"}):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        _, ids, scores, counts = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
+        assert ranker.last_stats["wide"] == 1 and (counts == k).all()
+        np.testing.assert_array_equal(ids.reshape(-1), oid, err_msg=f"{env} {ranker.last_stats}")
+        np.testing.assert_allclose(scores.reshape(-1), osc, rtol=3e-7, atol=1e-9)
+
+
 @pytest.mark.parametrize("splits", [None, "3"])
-@pytest.mark.parametrize(
-    "kernel_env",
-    [
-        {},
-        {"B200_TC_KERNEL": "2"},
-        {"B200_TC_KERNEL": "2", "B200_TC_STAGE": "0"},
-        {"B200_TC_KERNEL": "2", "B200_TC_TILE": "128"},
-        {"B200_TC_KERNEL": "2", "B200_TC_TILE": "128", "B200_TC_STAGE": "0"},
-        {"B200_TC_KERNEL": "1"},
-        # experimental kernel, not validated on hardware yet: B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k gen4
-        pytest.param({"B200_TC_KERNEL": "4"}, marks=pytest.mark.skipif(not os.environ.get("B200_TEST_EXPERIMENTAL"),
-                                                                         reason="tc4_topk.cuh is experimental")),
-    ],
-    ids=["gen3", "2sm256stage", "2sm256", "2sm128stage", "2sm128", "1sm", "gen4"],
-)
+@pytest.mark.parametrize("kernel_env", [{}, {"B200_EPI_WARPS": "16"}], ids=["epi8", "epi16"])
 def test_many_work_items_per_cta(rb, monkeypatch, splits, kernel_env):
-    """More subject tiles than CTAs (persistent loop, accumulator / list / threshold hand-over between work items) and
-    forced object splits, for every tensor-core kernel variant."""
+    """More subject tiles than CTA pairs (persistent loop, accumulator / list / threshold hand-over between work items) and
+    forced object splits, for both geometries of the fused kernel."""
     from rectools_b200 import _lib
 
     for k_, v_ in kernel_env.items():
@@ -236,7 +254,7 @@ def test_many_work_items_per_cta(rb, monkeypatch, splits, kernel_env):
     ranker = rb.B200Ranker("dot", u, i)
     sids = np.arange(n_users)
     _, ids, scores, counts = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
-    assert ranker.last_stats["path"] == 1
+    assert ranker.last_stats["path"] == 1 and ranker.last_stats["epi_warps"] == (16 if kernel_env else 8)
     sel = np.unique(np.concatenate([np.arange(0, n_users, 29), np.arange(n_users - 300, n_users)]))
     _, oid, osc = rank_oracle("dot", u, i, sel, k, csr[sel], accum="f64")
     np.testing.assert_array_equal(ids[sel].reshape(-1), oid, err_msg=str(ranker.last_stats))
@@ -245,6 +263,27 @@ def test_many_work_items_per_cta(rb, monkeypatch, splits, kernel_env):
     _, ids2, scores2, _ = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
     np.testing.assert_array_equal(ids, ids2)
     np.testing.assert_array_equal(scores, scores2)
+
+
+@pytest.mark.parametrize("distance, k, tc_mode", [("dot", 10, "auto"), ("cosine", 20, "auto"), ("dot", 20, "bf16"), ("dot", 5, "auto")])
+def test_random_vs_oracle_16_epilogue_warps(rb, monkeypatch, distance, k, tc_mode):
+    """The 16-warp geometry (four 16-slot lists per row) on the seeded random shapes."""
+    from rectools_b200 import _lib
+
+    monkeypatch.setenv("B200_EPI_WARPS", "16")
+    n_users, n_items, d = 3000, 40_000, 128
+    u, i = synth_factors(n_users, n_items, d, seed=k + 100)
+    csr = synth_viewed_csr(n_users, n_items, 60)
+    ranker = rb.B200Ranker(distance, u, i, tc_mode=tc_mode)
+    sids = np.arange(n_users)
+    _, ids, scores, counts = ranker.rank_padded(sids, k, csr, flags=_lib.Q_FORCE_TC)
+    assert ranker.last_stats["epi_warps"] == 16 and (counts == k).all()
+    _, oid, osc = rank_oracle(distance, u, i, sids, k, csr, accum="f64")
+    if distance == "cosine":
+        osc = osc * ranker.subjects_norms[np.repeat(sids, k)]
+    np.testing.assert_array_equal(ids.reshape(-1), oid, err_msg=str(ranker.last_stats))
+    np.testing.assert_allclose(scores.reshape(-1), osc, rtol=3e-7, atol=1e-9)
+    assert ranker.last_stats["n_fallback_rows"] <= n_users // 20, ranker.last_stats
 
 
 def test_edge_cases(rb):
@@ -266,11 +305,11 @@ def test_edge_cases(rb):
     for distance in ("dot", "cosine"):
         ranker = rb.B200Ranker(distance, u, i)
         for wl in (None, whitelist):
-            for k in (1, 10, 24, 33, None):
+            for k in (1, 10, 24, 33, 100, None):
                 for flags in (0, _lib.Q_FORCE_TC, _lib.Q_FORCE_EXACT):
                     n_pos = n_items if wl is None else len(wl)
                     k_eff = n_pos if k is None else min(k, n_pos)
-                    if flags == _lib.Q_FORCE_TC and k_eff > 24:
+                    if flags == _lib.Q_FORCE_TC and k_eff > 128:
                         continue
                     sids = np.arange(n_users)[::-1].copy()
                     s1, r1, c1 = ranker.rank(sids, k, csr[sids], wl) if flags == 0 else (None, None, None)
