@@ -1,18 +1,16 @@
 """CPU: `install()` / `uninstall()` rebind the ranker name that VectorModel / EASEModel use (vector.py:28, ease.py:31).
-Needs the reference checkout (build container only; skipped on the GPU box)."""
+Needs the reference package: the checkout (build container) or its staged copy oracle/_ref."""
 import os
 import sys
 
 import pytest
 
-REF = "/root/reference"
-STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "implicit_stub")
+from oracle import stage_reference
 
 
-@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "rectools")), reason="reference checkout not present")
-def test_install_rebinds_ranker(monkeypatch):
-    monkeypatch.syspath_prepend(REF)
-    monkeypatch.syspath_prepend(os.path.abspath(STUB))
+@pytest.mark.skipif(not stage_reference.available(), reason="reference package neither staged nor checked out")
+def test_install_rebinds_ranker():
+    added = stage_reference.add_to_path()
     import rectools.models.ease as ease
     import rectools.models.vector as vector
 
@@ -33,8 +31,7 @@ def test_install_rebinds_ranker(monkeypatch):
     finally:
         rectools_b200.uninstall()
     assert vector.ImplicitRanker is orig and ease.ImplicitRanker is orig
-    for m in [k for k in sys.modules if k.startswith("rectools.") or k == "rectools" or k.startswith("implicit")]:
-        sys.modules.pop(m, None)
+    stage_reference.remove_from_path(added)
 
 
 def test_distance_enum_matches_reference_values():

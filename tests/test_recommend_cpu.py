@@ -1,22 +1,21 @@
 """CPU: the vectorised `recommend()` returns the same table as the unmodified reference
 `ModelBase.recommend` (rectools/models/base.py:385-519).  The reference runs here through `oracle/implicit_stub`; the
 B200 ranker is replaced by the oracle-backed stand-in (`tests/helpers.OracleRanker`), so only the host logic is compared.
-Needs the reference checkout (build container only; skipped on the GPU box)."""
+Needs the reference package: the checkout (build container) or its staged copy oracle/_ref (GPU box)."""
 import os
 import sys
 
 import numpy as np
 import pytest
 
-REF = "/root/reference"
-STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "implicit_stub")
+from oracle import stage_reference
 
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "rectools")), reason="reference checkout not present")
+pytestmark = pytest.mark.skipif(not stage_reference.available(), reason="reference package neither staged nor checked out")
 
 
 @pytest.fixture(scope="module")
 def fitted():
-    sys.path[:0] = [REF, os.path.abspath(STUB)]
+    added = stage_reference.add_to_path()
     import pandas as pd
     from rectools import Columns
     from rectools.dataset import Dataset
@@ -35,11 +34,7 @@ def fitted():
     dataset = Dataset.construct(df)
     model = PureSVDModel(factors=8, random_state=0).fit(dataset)
     yield model, dataset, df
-    for m in [k for k in sys.modules if k.startswith("rectools.") or k == "rectools" or k.startswith("implicit")]:
-        sys.modules.pop(m, None)
-    for p_ in (REF, os.path.abspath(STUB)):
-        if p_ in sys.path:
-            sys.path.remove(p_)
+    stage_reference.remove_from_path(added)
 
 
 def _same(ref, got):
@@ -138,3 +133,37 @@ def test_recommend_to_items_repeated_targets_are_delegated(fitted):
     targets = np.concatenate([t, t[:1]])
     ref = model.recommend_to_items(targets, dataset, k=4)
     _same(ref, recommend_to_items(model, targets, dataset, 4, ranker_factory=OracleRanker))
+
+
+def test_repeated_users_are_delegated(fitted):
+    """ADVICE r1: with repeated target users the reference's rank column runs across the repeats (`groupby(user).cumcount()`,
+    base.py:778-791): the vectorised path hands such calls to the reference method."""
+    from rectools_b200.recommend import recommend
+    from tests.helpers import OracleRanker
+
+    model, dataset, _ = fitted
+    u = dataset.user_id_map.external_ids[:3]
+    users = np.array([u[0], u[1], u[0]])
+    ref = model.recommend(users, dataset, k=3, filter_viewed=True)
+    got = recommend(model, users, dataset, 3, True, ranker_factory=OracleRanker)
+    _same(ref, got)
+    assert got["rank"].max() == 6
+
+
+def test_viewed_csr_cache_notices_in_place_edits(fitted):
+    """VERDICT r1 #9: the cached viewed-items CSR is stamped with a digest of the (user, item) columns."""
+    from rectools_b200.recommend import viewed_csr
+
+    _, dataset, _ = fitted
+    a = viewed_csr(dataset)
+    assert viewed_csr(dataset) is a
+    df = dataset.interactions.df
+    old = df.loc[df.index[0], "item_id"]
+    new = (old + 1) % dataset.item_id_map.size
+    try:
+        df.loc[df.index[0], "item_id"] = new
+        b = viewed_csr(dataset)
+        assert b is not a and (b != a).nnz > 0
+    finally:
+        df.loc[df.index[0], "item_id"] = old
+    assert (viewed_csr(dataset) != a).nnz == 0
