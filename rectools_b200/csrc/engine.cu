@@ -333,8 +333,12 @@ int create_impl(b200_rank_engine** out, const void* objects, int32_t dtype, int6
             if (!p8.ok || !p16.ok) {
                 E->tc_dtype = B200_TC_OFF;
             } else {
-                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, p8.smem_bytes));
-                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p16.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p8.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p8.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p8.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<16, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p16.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p16.smem_bytes));
+                CK(cudaFuncSetAttribute(tc::fused_topk_kernel<16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, p16.smem_bytes));
             }
         }
         CK(cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -624,10 +628,19 @@ void run_tc(Call& c, const TcPass& t) {
     }
     const int grid = 2 * std::min(n_work, n_units);
     c.time_begin(0);
-    if (t.nw == 8)
-        tc::fused_topk_kernel<8><<<grid, tc::FusedCfg<8>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
-    else
-        tc::fused_topk_kernel<16><<<grid, tc::FusedCfg<16>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp);
+    const bool use_peers = t.peers && tp.n_peers > 0;  // (wide mode and threshold sharing never meet: sharing needs k <= 24)
+#define B200_LAUNCH(NW_, WIDE_, PEERS_) \
+    tc::fused_topk_kernel<NW_, WIDE_, PEERS_><<<grid, tc::FusedCfg<NW_>::THREADS, pl.smem_bytes, st>>>(tm_sub, tm_obj, tp)
+    if (t.nw == 8) {
+        if (t.wide) B200_LAUNCH(8, true, false);
+        else if (use_peers) B200_LAUNCH(8, false, true);
+        else B200_LAUNCH(8, false, false);
+    } else {
+        if (t.wide) B200_LAUNCH(16, true, false);
+        else if (use_peers) B200_LAUNCH(16, false, true);
+        else B200_LAUNCH(16, false, false);
+    }
+#undef B200_LAUNCH
     CK(cudaGetLastError());
     c.time_end();
     c.S.n_launches++;
@@ -1035,9 +1048,21 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         } else if (k_out <= 128) {
             k_cand = wide ? (c.nw == 16 ? 12 : 24) : (c.bf16 ? 30 : 25);  // wide: adaptive lists of phase 1;  else passes of 20
         }
+        if (shared && E->n_peers > 0 && k_out <= 24) {
+            // Shared thresholds: the pruning bound of a row is the MAXIMUM over all L = ranks x lists list minima, i.e. the
+            // largest K'-th best of L samples of N/L objects -- about global rank L K' - c_L L sqrt(K') (c_L = expected maximum
+            // of L standard normals).  The certificate needs that rank to stay above k plus a margin; everything beyond is
+            // wasted insertions (K' = 12 on 8 ranks sits near rank 100, K' = 6 near rank 27).
+            const int L = (E->n_peers + 1) * (c.nw / 4);
+            const double cL = L <= 2 ? 0.56 : L <= 4 ? 1.03 : L <= 8 ? 1.42 : L <= 16 ? 1.77 : L <= 32 ? 2.07 : 2.33;
+            const double target = k_out + std::max(12.0, 0.6 * k_out) + (c.bf16 ? 8.0 : 0.0);
+            int kc = 4;
+            while (kc < 32 && L * kc - cL * L * std::sqrt((double)kc) < target) ++kc;
+            k_cand = std::min(kc, c.nw == 16 ? 16 : 32);
+        }
         {
             const int forced = env_int("B200_TC_KCAND", 0);  // tuning hook
-            if (forced >= 4 && forced <= 32 && (forced >= k_out || c.nw == 16 || wide)) k_cand = forced;
+            if (forced >= 4 && forced <= 32 && (forced >= k_out || c.nw == 16 || wide || shared)) k_cand = forced;
         }
         bool use_tc = !sparse_sub && E->tc_dtype != B200_TC_OFF && k_cand > 0 && !(q->flags & B200_Q_FORCE_EXACT) && n_pos >= (int64_t)k_cand * 4;
         if (use_tc && !(q->flags & B200_Q_FORCE_TC)) {

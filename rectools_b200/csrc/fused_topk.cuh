@@ -40,8 +40,11 @@ struct FusedCfg {
     static constexpr int COLS = 1024 / NW;            // accumulator columns per epilogue thread and tile
     static constexpr int NLIST = NW / 4;              // column groups = candidate lists per row
     static constexpr int SLOTS = 64 / NLIST;          // list capacity (K' <= SLOTS)
-    static constexpr int REGS_LOW = NW == 8 ? 40 : 32;   // 32 * (REGS_LOW + NW/4 * REGS_EPI) <= 16384 per sub-partition
-    static constexpr int REGS_EPI = NW == 8 ? 232 : 120;
+    // setmaxnreg moves registers inside the CTA's LAUNCH allocation (168 x 384 = 64512, 96 x 640 = 61440), not the whole file:
+    // 4 * REGS_LOW + NW * REGS_EPI <= launch registers * (4 + NW).  (120 for the 16-warp geometry over-subscribes the pool: the
+    // last epilogue warps wait for ever in setmaxnreg.inc -- the first hardware run of round 2.)
+    static constexpr int REGS_LOW = NW == 8 ? 40 : 32;
+    static constexpr int REGS_EPI = NW == 8 ? 232 : 112;
     static constexpr int Q = NW == 8 ? 8 : 4;         // deferred hits per thread (ring FIFO), measured with the step period
     static constexpr int QSTRIDE = NW * 32 * 8;       // bytes between FIFO slots: [slot][epilogue thread] x (score, position)
     static constexpr int QBYTES = Q * QSTRIDE;
@@ -88,7 +91,7 @@ struct Sink {
 // look at the oldest pending hit of the row; drop it if the threshold has passed it; if it lies beyond the CSR window,
 // move the window (loads issued, not waited for) and leave the hit for the next step; otherwise test it against the
 // window / the exclusion list and hand it to the sink.
-template <int QN, int QS>
+template <int QN, int QS, bool WIDE>
 __device__ __forceinline__ void fifo_step(const TcParams& p, RowState& rs, CsrWindow& cw, uint32_t qaddr, int& head, int tail,
                                           uint32_t ls, uint32_t li, int kc, const Sink& sink) {
     if (head == tail) return;
@@ -121,7 +124,7 @@ __device__ __forceinline__ void fifo_step(const TcParams& p, RowState& rs, CsrWi
     ++head;
     const bool viewed = (g == cw.w0) | (g == cw.w1) | (g == cw.w2) | (g == cw.w3);
     if (!viewed && !(rs.xrow && is_excluded(rs, p.excl_n, g))) {
-        if (sink.appending) {
+        if (WIDE && sink.appending) {
             if (rs.cnt < sink.cap) {
                 sink.gs[rs.cnt] = val;
                 sink.gi[rs.cnt] = obj;
@@ -135,7 +138,9 @@ __device__ __forceinline__ void fifo_step(const TcParams& p, RowState& rs, CsrWi
 
 // Shared-memory map (dynamic, 1 KiB aligned): [KB] subject blocks | [NS] object blocks (16 KiB each: this CTA's half of a
 // 256-object tile) | candidate lists [NLIST][128 rows][SLOTS] scores + ids | FIFOs | thresholds [NLIST + 1][128] | barriers.
-template <int NW>
+// WIDE / PEERS compile the wide mode (threshold freeze + global append) and the peer-threshold exchange in; the plain
+// instantiation carries neither in its tile loop (measured: the run-time switches cost the 8-warp kernel ~6 %).
+template <int NW, bool WIDE, bool PEERS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FusedCfg<NW>::THREADS, 1)
 fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_constant__ CUtensorMap tm_obj, const TcParams p) {
     using Cfg = FusedCfg<NW>;
@@ -276,7 +281,7 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
         // slots, publish their maximum to this rank's global array, read the other ranks' published values (NVLink peer
         // loads, latency irrelevant here), leave their maximum in the row's extra exchange slot.  All values are monotone
         // lower bounds of the row's final threshold: a stale one is only weaker, never wrong.
-        if (p.n_peers > 0) {
+        if (PEERS && p.n_peers > 0) {
             const int h = (warp - 2) * 32 + lane;
             float published[2] = {-INFINITY, -INFINITY};
             uint32_t pub_tag[2] = {0xffffffffu, 0xffffffffu};
@@ -339,7 +344,8 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
         const uint32_t n_pos = (uint32_t)p.n_pos;
         const int kc = p.k_cand;  // (<= SLOTS, guaranteed by the host; a visible bound makes the compiler unroll the list scans fully and spill)
         const bool dbg_skip = p.debug_mode == 2;
-        const bool peers = p.n_peers > 0;
+        const bool peers = PEERS && p.n_peers > 0;
+        const uint32_t other_thr = pin(thr_row + (uint32_t)(colg ^ 1) * (TILE_M * 8));  // two lists per row: the other one's slot
         uint32_t buf = 0, tph = 0, work_tag = 0;  // accumulator buffer / its phase parity: tile_it & 1, (tile_it >> 1) & 1
         for (int w = pair; w < n_work; w += n_pairs, ++work_tag) {
             const int split = w / p.n_row_tiles, rt = w - split * p.n_row_tiles;
@@ -376,7 +382,7 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
                 window_load(p.indices, cw);
             };
             // (a macro, not a lambda: an outlined lambda would force every captured variable into local memory)
-#define B200_STEP() fifo_step<QN, QS>(p, rs, cw, qaddr, head, tail, ls, li, kc, sink)
+#define B200_STEP() fifo_step<QN, QS, WIDE>(p, rs, cw, qaddr, head, tail, ls, li, kc, sink)
             cursors_at(ts);
             int t = ts;
             uint32_t pos_t = (uint32_t)ts * TILE_N + (uint32_t)(colg * COLS);
@@ -386,22 +392,30 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
                 // previous work item out)
                 {
                     sts_thr(my_thr, work_tag, rs.thr);
+                    if constexpr (NLIST == 2) {
+                        uint32_t ptag;
+                        float pthr;
+                        lds_thr(other_thr, ptag, pthr);
+                        if (ptag == work_tag) rs.thr = fmaxf(rs.thr, pthr);
+                    } else {
 #pragma unroll
-                    for (int l = 0; l < NLIST; ++l) {
-                        if (NLIST == 2 && l == colg) continue;  // (four lists: reading the own slot back is cheaper than the branch)
-                        uint32_t ptag;
-                        float pthr;
-                        lds_thr(thr_row + (uint32_t)l * (TILE_M * 8), ptag, pthr);
-                        if (ptag == work_tag) rs.thr = fmaxf(rs.thr, pthr);
+                        for (int l = 0; l < NLIST; ++l) {  // (reading the own slot back is cheaper than a branch)
+                            uint32_t ptag;
+                            float pthr;
+                            lds_thr(thr_row + (uint32_t)l * (TILE_M * 8), ptag, pthr);
+                            if (ptag == work_tag) rs.thr = fmaxf(rs.thr, pthr);
+                        }
                     }
-                    if (peers) {
-                        uint32_t ptag;
-                        float pthr;
-                        lds_thr(thr_row + (uint32_t)NLIST * (TILE_M * 8), ptag, pthr);
-                        if (ptag == work_tag) rs.thr = fmaxf(rs.thr, pthr);
+                    if constexpr (PEERS) {
+                        if (peers) {
+                            uint32_t ptag;
+                            float pthr;
+                            lds_thr(thr_row + (uint32_t)NLIST * (TILE_M * 8), ptag, pthr);
+                            if (ptag == work_tag) rs.thr = fmaxf(rs.thr, pthr);
+                        }
                     }
                 }
-                if (it == p.phase1_tiles) {
+                if (WIDE && it == p.phase1_tiles) {
                     // wide mode: freeze the threshold.  Everything pending goes through the adaptive list first; then the
                     // list moves to the front of the row's global list and later candidates are appended behind it.
                     while (__any_sync(B200_FULL_MASK, head != tail)) B200_STEP();
@@ -488,7 +502,7 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
             }
             // ---- this thread's candidate list (unsorted), its length and its final threshold
             if (row_ok) {
-                if (!sink.appending) {
+                if (!(WIDE && sink.appending)) {
                     const int n = min(rs.cnt, kc);
                     for (int e = 0; e < n; ++e) {
                         sink.gs[e] = lds_f32(ls + e * 128);
@@ -500,7 +514,7 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
             }
             // last work item of this pair: lets the helper warps leave their polling loop (kept INSIDE the loop: any code behind
             // it made ptxas spill the staged accumulator, 1.5 KB of stack)
-            if (peers && w + n_pairs >= n_work) sts_thr(my_thr, TAG_DONE, INFINITY);
+            if (PEERS && peers && w + n_pairs >= n_work) sts_thr(my_thr, TAG_DONE, INFINITY);
         }
 #undef B200_STEP
     }

@@ -39,8 +39,11 @@ def viewed_csr(dataset: tp.Any) -> tp.Any:
     df = dataset.interactions.df
     key = id(df)
     # the CSR structure depends on the (user, item) columns only: their content digest catches in-place edits of the table
-    stamp = (len(df), content_hash(np.asarray(df[USER_COL].values)), content_hash(np.asarray(df[ITEM_COL].values)),
-             dataset.user_id_map.size, dataset.item_id_map.size)
+    try:
+        stamp = (len(df), content_hash(np.asarray(df[USER_COL].values)), content_hash(np.asarray(df[ITEM_COL].values)),
+                 dataset.user_id_map.size, dataset.item_id_map.size)
+    except (TypeError, KeyError, AttributeError):  # not a DataFrame (duck-typed datasets): identity of the table only
+        stamp = None
     hit = _CSR_CACHE.get(key)
     if hit is not None and hit[0]() is df and hit[2] == stamp:
         return hit[1]

@@ -86,21 +86,22 @@ def test_c5_shard_shape_d256_bf16_k20(rb):
 
 
 def test_second_chance_and_exhaustive_rerank_at_n1m(rb, catalogue_1m):
-    """Planted near-ties at N = 1M: for 32 subjects 12 objects within 1e-7 (relative) of each other sit on top (the K' = 12
-    lists cannot certify rank 10 -> second chance with 32 slots), for 8 subjects 80 EXACT duplicates (even 2 x 32 slots are
-    all ties at the cut -> exhaustive fp64 re-rank).  ids must equal the oracle's (score desc, id asc)."""
+    """Planted near-ties at N = 1M.  A list only fails its certificate when ties SATURATE it: for 32 subjects 40 objects within
+    ~1e-7 (relative) of each other sit on top -- ~20 per column half, more than the K' = 12 slots, fewer than the 32 of the
+    second-chance pass; for 8 subjects 80 EXACT duplicates -- ~40 per half, more than 32 slots: only the exhaustive fp64
+    re-rank can order them.  ids must equal the oracle's (score desc, id asc)."""
     from rectools_b200 import _lib
 
     items = catalogue_1m.copy()
     n_items = items.shape[0]
     users = gen_factors(4096, 128, 3)
     rng = np.random.default_rng(11)
-    free = rng.permutation(n_items)[: 32 * 12 + 8 * 80]
+    free = rng.permutation(n_items)[: 32 * 40 + 8 * 80]
     pos = 0
     for r in range(32):
         v = 1.5 * users[r] / np.linalg.norm(users[r])
-        for j in range(12):
-            items[free[pos]] = (v * np.float32(1.0 + 1e-7 * j)).astype(np.float32)
+        for j in range(40):
+            items[free[pos]] = (v * np.float32(1.0 + 1.2e-7 * j)).astype(np.float32)
             pos += 1
     for r in range(100, 108):
         v = (1.5 * users[r] / np.linalg.norm(users[r])).astype(np.float32)
