@@ -1033,8 +1033,11 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
         // list already gives ~2k candidates; rows where (nearly) all of the top-k fall into one column group fail the
         // certificate and take the second-chance pass.  Inserts, the dominant epilogue cost, scale with K'.
         c.bf16 = E->tc_dtype == B200_TC_BF16;
-        c.nw = env_int("B200_EPI_WARPS", 8) == 16 ? 16 : 8;
         const bool wide = k_out > 24 && k_out <= 128 && env_int("B200_WIDE", 1) != 0;
+        // 16 epilogue warps (B200_EPI_WARPS=16) measured 5 % slower at N = 1M, 5 % faster on a 125 K-object shard, equal at
+        // d = 256 (profiles/r02_ab_fused.txt): opt-in.  The wide mode always runs the 8-warp geometry: four lists per row
+        // freeze at a weaker, noisier rank and 10 % of the rows miss their candidate count.
+        c.nw = (!wide && env_int("B200_EPI_WARPS", 8) == 16) ? 16 : 8;
         int k_cand = 0;
         if (k_out <= 24) {
             if (c.nw == 16) {
@@ -1046,7 +1049,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
                 k_cand = std::min(32, k_out + surplus);
             }
         } else if (k_out <= 128) {
-            k_cand = wide ? (c.nw == 16 ? 12 : 24) : (c.bf16 ? 30 : 25);  // wide: adaptive lists of phase 1;  else passes of 20
+            k_cand = wide ? 24 : (c.bf16 ? 30 : 25);  // wide: adaptive lists of phase 1;  else passes of 20
         }
         if (shared && E->n_peers > 0 && k_out <= 24) {
             // Shared thresholds: the pruning bound of a row is the MAXIMUM over all L = ranks x lists list minima, i.e. the

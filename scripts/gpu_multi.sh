@@ -1,9 +1,9 @@
 #!/bin/bash
 # Multi-GPU check on N GPUs of one box: correctness of the sharded path under torchrun (NCCL, threshold sharing over
 # NVLink peer memory), then bench lines with and without sharing.
-# Usage: gpurun --gpus N --timeout 1200 -- 'bash scripts/gpu_multi.sh N [configs...]'
+# Usage: gpurun --gpus N --timeout 1200 -- 'bash scripts/gpu_multi.sh N [c2 c2:noshare c4 ...]'
 N=${1:-2}; shift
-CONFIGS=${@:-c2}
+CONFIGS=${@:-c2 c2:noshare}
 OUT=gpurun_out; mkdir -p $OUT; : > $OUT/multi_summary.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
@@ -22,12 +22,12 @@ except Exception as e:
 PY
 }
 port=29520
-for cfg in $CONFIGS; do
-  for share in share noshare; do
-    extra=""; [ "$share" = "noshare" ] && extra="--no-share"
-    port=$((port+1))
-    timeout 900 $TR --master-port $port bench.py --gpus $N --config $cfg --steps 5 --warmup 3 --parity-users 256 $extra > $OUT/bench_${cfg}_n${N}_${share}.log 2>&1
-    echo "$cfg n=$N $share: $(brief $OUT/bench_${cfg}_n${N}_${share}.log)" | tee -a $OUT/multi_summary.txt
-  done
+for item in $CONFIGS; do   # "c2" = with threshold sharing, "c2:noshare" = without
+  cfg=${item%%:*}; share=share; extra=""
+  if [ "$item" != "$cfg" ]; then share=noshare; extra="--no-share"; fi
+  port=$((port+1))
+  timeout 900 $TR --master-port $port bench.py --gpus $N --config $cfg --steps 5 --warmup 3 --parity-users 256 $extra > $OUT/bench_${cfg}_n${N}_${share}.log 2>&1
+  echo "$cfg n=$N $share: $(brief $OUT/bench_${cfg}_n${N}_${share}.log)" | tee -a $OUT/multi_summary.txt
+  grep '^{' $OUT/bench_${cfg}_n${N}_${share}.log | tail -n 1 > $OUT/r02_bench_${cfg}_n${N}_${share}.json
 done
 cat $OUT/multi_summary.txt

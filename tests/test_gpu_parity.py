@@ -183,7 +183,7 @@ def test_random_vs_oracle(rb, n_users, n_items, d, k, per_user, distance, tc_mod
             assert ranker.last_stats["n_fallback_rows"] <= max(4, n_users // 50), ranker.last_stats
 
 
-@pytest.mark.parametrize("mode", ["wide", "multipass", "wide16"])
+@pytest.mark.parametrize("mode", ["wide", "multipass"])
 @pytest.mark.parametrize("distance, k, use_wl", [("dot", 100, False), ("cosine", 100, True), ("dot", 37, False), ("cosine", 128, False)])
 def test_large_k_on_the_tensor_core_path(rb, monkeypatch, distance, k, use_wl, mode):
     """24 < k <= 128 on the tensor-core path (BASELINE config 3 shape: COSINE, K = 100, ~100 viewed).
@@ -194,8 +194,6 @@ def test_large_k_on_the_tensor_core_path(rb, monkeypatch, distance, k, use_wl, m
 
     if mode == "multipass":
         monkeypatch.setenv("B200_WIDE", "0")
-    if mode == "wide16":
-        monkeypatch.setenv("B200_EPI_WARPS", "16")
     n_users, n_items, d = 1500, 30_000, 64
     u, i = synth_factors(n_users, n_items, d, seed=k)
     csr = synth_viewed_csr(n_users, n_items, 100)

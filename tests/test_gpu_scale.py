@@ -42,8 +42,10 @@ def catalogue_1m():
     return gen_factors(1_000_000, 128, 1)
 
 
-def test_c2_shape_dot_k10_n1m(rb, catalogue_1m):
+def test_c2_shape_dot_k10_n1m(rb, catalogue_1m, monkeypatch):
     from rectools_b200 import _lib
+
+    monkeypatch.setenv("B200_TC_SPLITS", "1")  # two lists per row over the whole stream, as in a 1M-subject call
 
     items = catalogue_1m
     users = gen_factors(4096, 128, 0)
@@ -69,10 +71,11 @@ def test_c3_shape_cosine_k100_n1m(rb, catalogue_1m):
     eng.close()
 
 
-def test_c5_shard_shape_d256_bf16_k20(rb):
+def test_c5_shard_shape_d256_bf16_k20(rb, monkeypatch):
     """Config 5's per-GPU shard: 625 K items, d = 256, bf16 item embeddings handed over as a DEVICE tensor, K = 20."""
     import torch
 
+    monkeypatch.setenv("B200_TC_SPLITS", "1")
     n_items, d, k = 625_000, 256, 20
     items = torch.from_numpy(gen_factors(n_items, d, 1)).to(torch.bfloat16)
     users = torch.from_numpy(gen_factors(4096, d, 0)).to(torch.bfloat16).float()
@@ -85,13 +88,14 @@ def test_c5_shard_shape_d256_bf16_k20(rb):
     _check(ranker, "dot", users.numpy(), items.float().numpy(), k, csr, ids, scores, counts)
 
 
-def test_second_chance_and_exhaustive_rerank_at_n1m(rb, catalogue_1m):
+def test_second_chance_and_exhaustive_rerank_at_n1m(rb, catalogue_1m, monkeypatch):
     """Planted near-ties at N = 1M.  A list only fails its certificate when ties SATURATE it: for 32 subjects 40 objects within
     ~1e-7 (relative) of each other sit on top -- ~20 per column half, more than the K' = 12 slots, fewer than the 32 of the
     second-chance pass; for 8 subjects 80 EXACT duplicates -- ~40 per half, more than 32 slots: only the exhaustive fp64
     re-rank can order them.  ids must equal the oracle's (score desc, id asc)."""
     from rectools_b200 import _lib
 
+    monkeypatch.setenv("B200_TC_SPLITS", "1")  # (object splits would spread the planted ties over 2 x splits lists)
     items = catalogue_1m.copy()
     n_items = items.shape[0]
     users = gen_factors(4096, 128, 3)
