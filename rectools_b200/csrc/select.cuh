@@ -363,6 +363,10 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) rescore_select_kernel(const Se
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(B200_FULL_MASK, total, o);
 
+    // approximate scores are in units scaled by 2^(row_exp + obj_exp); row_exp is indexed by batch row
+    const int ex = (p.row_exp ? p.row_exp[sel] : 0) + p.obj_exp;
+    const double eps = (double)p.eps_rel * sqrt(unorm2) * (double)p.max_obj_norm;
+    const double eps_scaled = ldexp(eps, ex);
     float run_s = -INFINITY;
     int run_i = B200_PAD_ID;
     int n_valid = 0;
@@ -380,12 +384,28 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) rescore_select_kernel(const Se
         }
         bool valid = list >= 0;
         int id = B200_PAD_ID;
+        float approx = -INFINITY;
         if (valid) {
-            id = p.in_ids[((int64_t)list * p.list_stride_rows + sel) * p.L + e];
+            const int64_t o = ((int64_t)list * p.list_stride_rows + sel) * p.L + e;
+            id = p.in_ids[o];
             valid = id != B200_PAD_ID && id >= 0;
+            if (valid) approx = p.in_scores[o];
         }
-        float s = exact_score(p, sub, valid ? id : 0);
-        valid = valid && (s < bs || (s == bs && id > bi));
+        // Candidates that provably cannot reach the top-kp are not re-scored (their 512-byte rows are not gathered): with
+        // |approx - exact| <= eps for every candidate, one whose approximate score lies more than 2 eps below the kp-th best
+        // approximate score ranks below kp others.  (Single-round rows of a first pass only.)
+        bool skip = false;
+        if (p.k0 == 0 && total <= 32) {
+            float sa = approx;
+            int si = lane;
+            warp_sort32(sa, si, lane);
+            const float a_k = __shfl_sync(B200_FULL_MASK, sa, p.kp - 1);  // -inf with fewer than kp candidates: nothing is skipped
+            skip = valid && (double)approx < (double)a_k - 2.0 * eps_scaled * (1.0 + 1e-6);
+        }
+        float s = -INFINITY;
+        if (valid && !skip) s = exact_score(p, sub, id);
+        valid = valid && !skip && (s < bs || (s == bs && id > bi));
+        n_valid += __popc(__ballot_sync(B200_FULL_MASK, skip));  // still candidates of the row (the certificate counts them)
         if (!valid) {
             s = -INFINITY;
             id = B200_PAD_ID;
@@ -403,10 +423,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) rescore_select_kernel(const Se
     }
     if (lane == 0) p.out_counts[lrow] = p.k0 + n_out;
 
-    // approximate scores are in units scaled by 2^(row_exp + obj_exp); row_exp is indexed by batch row
-    const int ex = (p.row_exp ? p.row_exp[sel] : 0) + p.obj_exp;
     const double thr = ldexp((double)thr_max, -ex);
-    const double eps = (double)p.eps_rel * sqrt(unorm2) * (double)p.max_obj_norm;
     if (p.out_bounds) {
         // one fp32 ulp of slack: a discarded object whose exact score rounds up to e_k could tie with a smaller id
         if (lane == 0)
