@@ -127,7 +127,8 @@ typedef struct b200_rank_query {
 } b200_rank_query;
 
 typedef struct b200_rank_stats {
-    int32_t path;            /* 0 = exhaustive fp64 kernel, 1 = tensor-core candidates + fp64 re-score */
+    int32_t path;            /* 0 = exhaustive fp64 kernel, 1 = tensor-core candidates + fp64 re-score, 2 = sparse subjects (SpMM
+                              * scores + streaming selection), 3 = k > 128: exhaustive scores materialised once + selection passes */
     int32_t tc_dtype;        /* B200_TC_FP16 / B200_TC_BF16 when path == 1 */
     int32_t k_out;           /* columns of the output arrays */
     int32_t k_cand;          /* candidates kept per row and item split by the tensor-core pass */

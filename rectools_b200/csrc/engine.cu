@@ -724,6 +724,37 @@ void run_sparse(Call& c, const int64_t* sp_indptr, const int32_t* sp_indices, co
     }
 }
 
+// Dense subjects with k > 128: one exhaustive scoring of bounded row chunks into HBM + k / 32 streaming selection passes.
+void run_dense_large_k(Call& c, const float* sub32, const int64_t* rowmap, const int64_t* f_indptr, int64_t nr, int32_t* o_ids,
+                       float* o_scores, int32_t* o_counts) {
+    b200_rank_engine* E = c.E;
+    cudaStream_t st = c.st;
+    const int64_t rows_max = std::max<int64_t>(32, std::min<int64_t>(nr, ((int64_t)1 << 30) / std::max<int64_t>(4 * c.n_pos, 1)) / 32 * 32);
+    E->sp_scores.ensure(sizeof(float) * (size_t)rows_max * c.n_pos);
+    for (int64_t b0 = 0; b0 < nr; b0 += rows_max) {
+        const int64_t nb = std::min(rows_max, nr - b0);
+        const int blocks_x = grid_for(nb, 32);
+        const int64_t tiles_total = (c.n_pos + 31) / 32;
+        const int splits = (int)std::max<int64_t>(1, std::min<int64_t>((4 * E->sm_count + blocks_x - 1) / blocks_x, tiles_total));
+        c.time_begin(0);
+        dense_scores_kernel<<<dim3((unsigned)blocks_x, (unsigned)splits), 256, 0, st>>>(
+            rowmap ? sub32 : sub32 + b0 * c.d, rowmap ? rowmap + b0 : nullptr, nb, E->obj32_ptr, c.wl, c.n_pos, c.d, c.norms(),
+            E->sp_scores.as<float>());
+        CK(cudaGetLastError());
+        c.time_end();
+        c.S.n_launches++;
+        for (int k0 = 0; k0 < c.k_out; k0 += 32) {
+            c.time_begin(1);
+            scores_topk_kernel<<<grid_for(nb * 32, 256), 256, 0, st>>>(E->sp_scores.as<float>(), nb, c.n_pos, c.wl, f_indptr ? f_indptr + b0 : nullptr,
+                                                                      c.indices, (int32_t)E->id_offset, c.k_out, k0, std::min(32, c.k_out - k0),
+                                                                      o_ids + b0 * c.k_out, o_scores + b0 * c.k_out, o_counts + b0);
+            CK(cudaGetLastError());
+            c.time_end();
+            c.S.n_launches++;
+        }
+    }
+}
+
 int32_t read_counter(Call& c, const int32_t* dev) {
     CK(cudaMemcpyAsync(c.E->h_pinned, dev, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
     CK(cudaStreamSynchronize(c.st));
@@ -1058,7 +1089,7 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             // wasted insertions (K' = 12 on 8 ranks sits near rank 100, K' = 6 near rank 27).
             const int L = (E->n_peers + 1) * (c.nw / 4);
             const double cL = L <= 2 ? 0.56 : L <= 4 ? 1.03 : L <= 8 ? 1.42 : L <= 16 ? 1.77 : L <= 32 ? 2.07 : 2.33;
-            const double target = k_out + std::max(12.0, 0.6 * k_out) + (c.bf16 ? 8.0 : 0.0);
+            const double target = k_out + std::max(12.0, 0.6 * k_out) + (c.bf16 ? 20.0 : 0.0);
             int kc = 4;
             while (kc < 32 && L * kc - cL * L * std::sqrt((double)kc) < target) ++kc;
             k_cand = std::min(kc, c.nw == 16 ? 16 : 32);
@@ -1105,6 +1136,13 @@ int b200_rank_topk(b200_rank_engine* E, const b200_rank_query* q, b200_rank_stat
             if (sparse_sub) {
                 S.path = 2;
                 run_sparse(c, sp_indptr + r0, sp_indices, sp_data, nr, ip, oi, os, oc);
+            } else if (!use_tc && k_out > 128) {
+                S.path = 3;  // materialised exhaustive scores + streaming selection passes
+                run_dense_large_k(c, sub, rm, ip, nr, oi, os, oc);
+                if (c.o_bounds) {
+                    fill_f32_kernel<<<grid_for(nr, 256), 256, 0, st>>>(c.o_bounds + r0, nr, -INFINITY);
+                    CK(cudaGetLastError());
+                }
             } else if (!use_tc) {
                 S.path = 0;
                 run_exact(c, nullptr, nr, sub, rm, ip, oi, os, oc, 0, k_out, true);

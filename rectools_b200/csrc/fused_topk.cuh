@@ -315,14 +315,19 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
                         published[s] = own;
                         stg_peer(p.peer_pub + p.peer_row0 + grow, p.peer_epoch, ldexpf(own, -p.peer_exp));
                     }
+                    // all peer loads in flight at once: one NVLink round trip per row and round (issued one after the other the
+                    // seven loads took ~15 us -- 20 tiles -- and the shared thresholds arrived after the warm-up they are meant
+                    // to shorten: first 8-GPU measurement of round 2)
+                    unsigned long long v[MAX_PEERS];
+#pragma unroll
+                    for (int q = 0; q < MAX_PEERS; ++q) v[q] = q < p.n_peers ? ldg_peer(p.peer_in[q] + p.peer_row0 + grow) : 0ull;
                     float best = -INFINITY;
-                    for (int q = 0; q < p.n_peers; ++q) {
-                        const unsigned long long v = ldg_peer(p.peer_in[q] + p.peer_row0 + grow);
-                        if ((uint32_t)(v >> 32) == p.peer_epoch) best = fmaxf(best, __uint_as_float((uint32_t)v));
-                    }
+#pragma unroll
+                    for (int q = 0; q < MAX_PEERS; ++q)
+                        if (q < p.n_peers && (uint32_t)(v[q] >> 32) == p.peer_epoch) best = fmaxf(best, __uint_as_float((uint32_t)v[q]));
                     if (best > -INFINITY) sts_thr(smem_u32(sThr + NLIST * TILE_M + r), tag, ldexpf(best, p.peer_exp));
                 }
-                __nanosleep(400);
+                __nanosleep(200);
             }
         }
     } else if (warp >= Cfg::EPI0) {

@@ -66,6 +66,62 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_scores_kernel(const int64_t
         if (obj[c] >= 0) scores[row * n_pos + pos0 + c] = (float)acc[c];
 }
 
+// Dense subjects, k > 128 (k = None: "all objects", rank_implicit.py:233-234): score rows are materialised ONCE with the
+// exhaustive kernel's arithmetic (fp64-accumulated dot, / norm for COSINE, rounded to fp32) and the k / 32 selection passes
+// stream 4-byte scores instead of repeating 2 d fp64 FLOP per object and pass.
+// Block = 32 subjects x 32 positions per step (lane = position), grid (row blocks, position splits).
+constexpr int DS_DK = 64;
+
+__global__ void __launch_bounds__(256) dense_scores_kernel(const float* __restrict__ subjects, const int64_t* __restrict__ row_map,
+                                                           int64_t n_rows, const float* __restrict__ objects,
+                                                           const int32_t* __restrict__ pos2obj, int64_t n_pos, int32_t d,
+                                                           const float* __restrict__ obj_norms, float* __restrict__ scores) {
+    __shared__ float s_obj[32][DS_DK + 1];
+    __shared__ float s_sub[32][DS_DK];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    const int64_t tiles_total = (n_pos + 31) >> 5;
+    const int64_t tiles_per = (tiles_total + gridDim.y - 1) / gridDim.y;
+    const int64_t t0 = blockIdx.y * tiles_per, t1 = min(t0 + tiles_per, tiles_total);
+    for (int64_t t = t0; t < t1; ++t) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int dk0 = 0; dk0 < d; dk0 += DS_DK) {
+            __syncthreads();
+            for (int e = tid; e < 32 * DS_DK; e += 256) {
+                const int it = e >> 6, j = e & (DS_DK - 1);
+                const int64_t pos = t * 32 + it;
+                float v = 0.f;
+                if (pos < n_pos && dk0 + j < d) {
+                    const int64_t obj = pos2obj ? (int64_t)pos2obj[pos] : pos;
+                    v = __ldg(objects + obj * d + dk0 + j);
+                }
+                s_obj[it][j] = v;
+                const int64_t r = row0 + it;
+                float u = 0.f;
+                if (r < n_rows && dk0 + j < d) u = __ldg(subjects + (row_map ? row_map[r] : r) * d + dk0 + j);
+                s_sub[it][j] = u;
+            }
+            __syncthreads();
+            const int jn = min(DS_DK, d - dk0);
+            for (int j = 0; j < jn; ++j) {
+                const double ov = (double)s_obj[lane][j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = fma(ov, (double)s_sub[warp * 4 + q][j], acc[q]);
+            }
+        }
+        const int64_t pos = t * 32 + lane;
+        if (pos < n_pos) {
+            const int obj = pos2obj ? pos2obj[pos] : (int)pos;
+            const double nrm = obj_norms ? (double)__ldg(obj_norms + obj) : 1.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t r = row0 + warp * 4 + q;
+                if (r < n_rows) scores[r * n_pos + pos] = obj_norms ? (float)(acc[q] / nrm) : (float)acc[q];
+            }
+        }
+    }
+}
+
 // One warp per row: streaming top-kp (kp <= 32) over a materialised score row, order (score desc, id asc), objects listed
 // in the row's filter_pairs_csr slice never returned; entries [k0, k0 + kp) of a k > 32 query are bounded by the previous
 // pass's last entry exactly as in exact_topk_kernel.

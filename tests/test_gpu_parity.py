@@ -480,3 +480,23 @@ def test_implicit_gpu_shim_topk(rb, cosine):
     np.testing.assert_array_equal(ids[valid], oid[valid])
     np.testing.assert_allclose(scores[valid], osc[valid], rtol=3e-7, atol=1e-9)
     assert (scores[~valid] <= -3.0e38).all()
+
+
+def test_k_none_and_k_above_128_materialised_scores(rb):
+    """`k=None` (all objects, rank_implicit.py:233-234) and k > 128: the exhaustive scores are materialised once and the
+    k / 32 selection passes stream them (path 3) -- whitelist, filter, COSINE, rows with fewer than k survivors."""
+    n_users, n_items, d = 500, 6_000, 48
+    u, i = synth_factors(n_users, n_items, d, seed=8)
+    i[100:130] = i[100]
+    csr = synth_viewed_csr(n_users, n_items, 60)
+    wl = np.sort(np.random.default_rng(2).choice(n_items, 2_500, replace=False))
+    sids = np.random.default_rng(3).permutation(n_users)[:300]
+    for distance in ("dot", "cosine"):
+        ranker = rb.B200Ranker(distance, u, i)
+        for k, whitelist in ((None, wl), (300, None), (1000, wl)):
+            subj, ids, scores = ranker.rank(sids, k, csr[sids], whitelist)
+            assert ranker.last_stats["path"] == 3, ranker.last_stats
+            es, eid, esc = rank_oracle(distance, u, i, sids, k, csr[sids], whitelist, accum="f64")
+            np.testing.assert_array_equal(subj, es)
+            np.testing.assert_array_equal(ids, eid, err_msg=f"{distance} k={k}")
+            np.testing.assert_allclose(scores, esc, rtol=1e-6, atol=1e-7)
