@@ -143,6 +143,27 @@ class EngineShard:
             out.scores[:, :k_loc] = sc
         return st
 
+    def merge_into(self, g: tp.Any, w: int, n: int, k: int, certified: bool, o_ids, o_sc, o_cnt, fail_rows, fail_count) -> None:
+        """Merge `w` packed buffers of `n` rows each (one after the other in `g`) into the given output tensors; with
+        `certified` the rows the global certificate rejects are listed in `fail_rows` / counted in `fail_count` (zeroed here)."""
+        from . import _lib
+
+        torch = self.torch
+        base = g.data_ptr()
+        stride = n * (2 * k + 2)
+        fail_count.zero_()
+        args = (self.device.index, torch.cuda.current_stream().cuda_stream, w, n, k, base, base + 4 * n * k, base + 8 * n * k)
+        if certified and k <= 32:
+            _lib.check(_lib.load().b200_rank_merge_certified(
+                *args, base + 8 * n * k + 4 * n, stride, o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(), fail_rows.data_ptr(),
+                fail_count.data_ptr()))
+        else:
+            ids, sc, cnt, _ = Packed.views(torch, g, w, n, k)
+            ids, sc, cnt = ids.contiguous(), sc.contiguous(), cnt.contiguous()
+            _lib.check(_lib.load().b200_rank_merge(
+                self.device.index, torch.cuda.current_stream().cuda_stream, w, n, k, ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(),
+                o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr()))
+
     def merge(self, g: tp.Any, w: int, n: int, k: int, certified: bool):
         """Merge `w` gathered packed buffers; returns (ids, scores, counts, fail_rows, fail_count) device tensors."""
         from . import _lib
@@ -253,26 +274,66 @@ class ShardedB200Ranker:
 
     # ------------------------------------------------------------------------------------------------------------
     def _exchange(self, pk: tp.Any, n: int, k: int, shared: bool, rerank: tp.Optional[tp.Callable[..., tp.Any]]):
-        """All-gather the packed local results of my subject group, merge, re-rank rows the global certificate rejects."""
+        """Exchange + merge of my subject group's packed local results (the optimised collective): an ALL-TO-ALL by
+        subject slice -- rank j receives every shard's lists of rows [j n/w, (j+1) n/w) and merges only those (1/w of the
+        merge work, (w-1)/w x one buffer inbound instead of (w-1) buffers) -- then ONE all-gather of the merged slices (with
+        the rows the global certificate rejected).  Rejected rows are re-ranked without threshold sharing on every rank."""
         torch, w = self.torch, self.item_shards
         if w == 1:
             return pk.ids, pk.scores, pk.counts
-        g = torch.empty((w * pk.stride,), dtype=torch.int32, device=pk.buf.device)
-        self.dist.all_gather_into_tensor(g, pk.buf, group=self.exchange_group)
+        dev = pk.buf.device
+        per = -(-n // w)  # rows per slice (the last slices may be short or empty: padded with empty rows)
+        sect = per * (2 * k + 2)
+        # ---- by destination: [w][ids per*k | scores per*k | counts per | bounds per]
+        send = torch.empty((w, sect), dtype=torch.int32, device=dev)
+
+        def by_slice(t, width, fill):
+            """[n, width] section -> [w, per * width] (rows beyond n: `fill`)."""
+            if per * w == n:
+                return t.reshape(w, per * width)
+            out = torch.full((w * per, width), fill, dtype=t.dtype, device=dev)
+            out[:n] = t.reshape(n, width)
+            return out.view(w, per * width)
+
+        send[:, : per * k] = by_slice(pk.ids, k, -1)
+        send[:, per * k : 2 * per * k] = by_slice(pk.scores, k, NEG_MAX).view(torch.int32)
+        send[:, 2 * per * k : 2 * per * k + per] = by_slice(pk.counts, 1, 0)
+        send[:, 2 * per * k + per :] = by_slice(pk.bounds, 1, float("-inf")).view(torch.int32)
+        recv = torch.empty((w * sect,), dtype=torch.int32, device=dev)
+        self.dist.all_to_all_single(recv, send.view(-1), group=self.exchange_group)
+        # ---- merge my slice; [ids | scores | counts | failed rows | n failed] goes round
+        out_len = per * (2 * k + 2) + 2
+        mine = torch.zeros((out_len,), dtype=torch.int32, device=dev)
+        m_ids = mine[: per * k].view(per, k)
+        m_sc = mine[per * k : 2 * per * k].view(torch.float32).view(per, k)
+        m_cnt = mine[2 * per * k : 2 * per * k + per]
+        m_fail = mine[2 * per * k + per : 2 * per * k + 2 * per]
+        m_nfail = mine[2 * per * k + 2 * per : 2 * per * k + 2 * per + 1]
         if self.host_provider:
-            ids, sc, cnt, _ = Packed.views(torch, g, w, n, k)
+            ids, sc, cnt, _ = Packed.views(torch, recv, w, per, k)
             o = merge_padded_numpy(ids.numpy(), sc.numpy(), cnt.numpy(), k)
-            return tuple(torch.from_numpy(x) for x in o)
-        o_ids, o_sc, o_cnt, fail_rows, fail_count = self.local.merge(g, w, n, k, certified=shared)
-        n_fail = int(fail_count.item()) if shared else 0
-        self.last_stats["n_uncertified_rows"] = n_fail
-        if n_fail:
-            rows = fail_rows[:n_fail].sort().values.long()
-            pk2 = rerank(rows)  # local, self-certified lists of those rows
-            g2 = torch.empty((w * pk2.stride,), dtype=torch.int32, device=pk.buf.device)
-            self.dist.all_gather_into_tensor(g2, pk2.buf, group=self.exchange_group)
-            r_ids, r_sc, r_cnt, _, _ = self.local.merge(g2, w, n_fail, k, certified=False)
-            o_ids[rows], o_sc[rows], o_cnt[rows] = r_ids, r_sc, r_cnt
+            m_ids[:], m_sc[:], m_cnt[:] = (torch.from_numpy(x) for x in o)
+        else:
+            self.local.merge_into(recv, w, per, k, shared, m_ids, m_sc, m_cnt, m_fail, m_nfail)
+        allm = torch.empty((w, out_len), dtype=torch.int32, device=dev)
+        self.dist.all_gather_into_tensor(allm.view(-1), mine, group=self.exchange_group)
+        o_ids = allm[:, : per * k].reshape(w * per, k)[:n]
+        o_sc = allm[:, per * k : 2 * per * k].view(torch.float32).reshape(w * per, k)[:n]
+        o_cnt = allm[:, 2 * per * k : 2 * per * k + per].reshape(w * per)[:n]
+        n_fail = 0
+        if shared and not self.host_provider:
+            counts = allm[:, 2 * per * k + 2 * per].cpu().tolist()  # (the one host read-back of the exchange)
+            n_fail = int(sum(counts))
+            self.last_stats["n_uncertified_rows"] = n_fail
+            if n_fail:
+                fails = allm[:, 2 * per * k + per : 2 * per * k + 2 * per]
+                rows = torch.cat([fails[j, :c].long() + j * per for j, c in enumerate(counts) if c]).sort().values
+                pk2 = rerank(rows)  # local, self-certified lists of those rows
+                g2 = torch.empty((w * pk2.stride,), dtype=torch.int32, device=dev)
+                self.dist.all_gather_into_tensor(g2, pk2.buf, group=self.exchange_group)
+                r_ids, r_sc, r_cnt, _, _ = self.local.merge(g2, w, n_fail, k, certified=False)
+                o_ids, o_sc, o_cnt = o_ids.contiguous(), o_sc.contiguous(), o_cnt.contiguous()
+                o_ids[rows], o_sc[rows], o_cnt[rows] = r_ids, r_sc, r_cnt
         return o_ids, o_sc, o_cnt
 
     def _collect(self, o_ids: tp.Any, o_sc: tp.Any, o_cnt: tp.Any, row_bounds: tp.Sequence[tp.Tuple[int, int]], k: int):
