@@ -445,33 +445,9 @@ fused_topk_kernel(const __grid_constant__ CUtensorMap tm_sub, const __grid_const
                     tc_fence_before();
                     __syncwarp();
                     if (lane0) mbar_arrive_cluster(buf ? tempty1 : tempty0);  // accumulator free again
-                    // First tile of a work item: the lists are empty and EVERY column would be a hit (128 extractions per row,
-                    // ~70 tile times of epilogue work -- 1.5 % of a 1M-object stream, 12 % of a 125 K-object shard).  The K'-th
-                    // largest of the slice's group maxima (distinct columns) is a lower bound of the slice's K'-th best score:
-                    // seed the threshold with it and only ~K' .. 2 K' columns are extracted.  (Tiles with padded positions are
-                    // left alone: their zero scores are not candidates.)
-                    if (it == 0 && kc <= COLS / 8 && pos_t + (uint32_t)COLS <= n_pos) {
-                        float g[COLS / 8];
-                        {
-                            float q[4];
-                            chunk_groups<0>(r, q);
-                            g[0] = q[0], g[1] = q[1], g[2] = q[2], g[3] = q[3];
-                            chunk_groups<32>(r, q);
-                            g[4] = q[0], g[5] = q[1], g[6] = q[2], g[7] = q[3];
-                        }
-                        if constexpr (COLS == 128) {
-                            float q[4];
-                            chunk_groups<64>(r, q);
-                            g[8] = q[0], g[9] = q[1], g[10] = q[2], g[11] = q[3];
-                            chunk_groups<96>(r, q);
-                            g[12] = q[0], g[13] = q[1], g[14] = q[2], g[15] = q[3];
-                        }
-                        const float seed = kth_largest(g, kc);
-                        // one ulp below (towards -inf): the columns that EQUAL the seed stay hits of the strict comparison
-                        const uint32_t sb = __float_as_uint(seed);
-                        const float below = seed > 0.f ? __uint_as_float(sb - 1u) : seed < 0.f ? __uint_as_float(sb + 1u) : -1e-30f;
-                        rs.thr = fmaxf(rs.thr, below);
-                    }
+                    // (Measured and not kept: seeding the first tile's threshold with the K'-th largest group maximum -- the lists
+                    // are empty there and every column is a hit -- changed nothing at N = 1M and gained 1.3 % on a 125 K-object
+                    // shard, profiles/r02_ab_fused.txt.)
                     if constexpr (COLS == 128) {
                         const float m0 = chunk_max<0>(r), m1 = chunk_max<32>(r), m2 = chunk_max<64>(r), m3 = chunk_max<96>(r);
                         const float mx = fmaxf(max3(m0, m1, m2), m3);

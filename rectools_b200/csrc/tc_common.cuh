@@ -392,43 +392,6 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[NR]) {
     return fmaxf(max3(g0, g1, g2), g3);
 }
 
-// The four group maxima of chunk OFF (columns 0-8, 9-17, 18-26, 27-31): each is attained by a distinct column.
-template <int OFF, int NR>
-__device__ __forceinline__ void chunk_groups(const uint32_t (&r)[NR], float (&g)[4]) {
-    g[0] = max3(max3(fu(r[OFF + 0]), fu(r[OFF + 1]), fu(r[OFF + 2])), max3(fu(r[OFF + 3]), fu(r[OFF + 4]), fu(r[OFF + 5])),
-                max3(fu(r[OFF + 6]), fu(r[OFF + 7]), fu(r[OFF + 8])));
-    g[1] = max3(max3(fu(r[OFF + 9]), fu(r[OFF + 10]), fu(r[OFF + 11])), max3(fu(r[OFF + 12]), fu(r[OFF + 13]), fu(r[OFF + 14])),
-                max3(fu(r[OFF + 15]), fu(r[OFF + 16]), fu(r[OFF + 17])));
-    g[2] = max3(max3(fu(r[OFF + 18]), fu(r[OFF + 19]), fu(r[OFF + 20])), max3(fu(r[OFF + 21]), fu(r[OFF + 22]), fu(r[OFF + 23])),
-                max3(fu(r[OFF + 24]), fu(r[OFF + 25]), fu(r[OFF + 26])));
-    g[3] = max3(max3(fu(r[OFF + 27]), fu(r[OFF + 28]), fu(r[OFF + 29])), fu(r[OFF + 30]), fu(r[OFF + 31]));
-}
-
-// The k-th largest (k = 1 .. N) of N = 8 or 16 values: bitonic sort network (descending) + a select tree for the run-time k.
-template <int N>
-__device__ __forceinline__ float kth_largest(float (&v)[N], int k) {
-#pragma unroll
-    for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int j = i ^ stride;
-                if (j > i) {
-                    const bool desc = (i & size) == 0;  // this pair puts the larger value first
-                    const float a = v[i], b = v[j];
-                    v[i] = desc ? fmaxf(a, b) : fminf(a, b);
-                    v[j] = desc ? fminf(a, b) : fmaxf(a, b);
-                }
-            }
-        }
-    }
-    float out = v[0];
-#pragma unroll
-    for (int i = 1; i < N; ++i) out = (k - 1 == i) ? v[i] : out;
-    return out;
-}
-
 template <int OFF, int J0, int J1, int NR>
 __device__ __forceinline__ unsigned group_mask(const uint32_t (&r)[NR], float thr) {
     unsigned m = 0;
