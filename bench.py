@@ -16,8 +16,8 @@ items per user).  Named workloads (BASELINE.json `configs[1..4]`; the default is
            matrices): per step the users' factors + CSR filter are copied from pinned host memory and the K (id, score)
            pairs copied back
   N > 1  : the catalogue is item-sharded over the ranks (north_star) through `rectools_b200.sharded.ShardedB200Ranker`: every
-           rank scores all users against its shard (thresholds shared over NVLink peer memory), ONE NCCL all-gather of the
-           packed results + a certifying merge kernel; total work is fixed => "scaling": "strong"
+           rank scores all users against its shard (thresholds shared over NVLink peer memory), an NCCL all-to-all by user
+           slice + a certifying merge kernel + an all-gather of the merged slices; total work is fixed => "scaling": "strong"
   model_recommend : `ImplicitALSWrapperModel.recommend()` of the UNMODIFIED reference (staged in oracle/_ref) after
            `rectools_b200.install()`, users/sec incl. the host code around the ranker (N = 1, when the package is staged)
   --impl reference : the reference's CPU path (restatement of implicit.cpu.topk: BLAS sgemm + OpenMP select, all host
@@ -464,8 +464,8 @@ def main():
             "value": n_users_all * e2e_steps / (e2e_ms / 1e3), "unit": "users/s", "steps": e2e_steps,
             "h2d_bytes_per_step": int(e2e_bytes[0]), "d2h_bytes_per_step": int(e2e_bytes[1]),
             "api": ("rectools_b200.Engine.topk (C ABI b200_rank_topk) with pinned host buffers" if world == 1 else
-                    "rectools_b200.sharded.ShardedB200Ranker.rank_device with pinned host matrices (per rank: C ABI b200_rank_topk, one "
-                    "NCCL all-gather, b200_rank_merge_certified), merged result copied to the host on rank 0"),
+                    "rectools_b200.sharded.ShardedB200Ranker.rank_device with pinned host matrices (per rank: C ABI b200_rank_topk, NCCL "
+                    "all-to-all + b200_rank_merge_certified + all-gather), merged result copied to the host on rank 0"),
             "engine_ms_last_step": dict(e2e_stats),
         }
         step_resident()  # leave the resident result in `result` for the parity sample
@@ -604,7 +604,7 @@ def main():
             "parallelism": (
                 "single GPU" if world == 1 else
                 f"items sharded over {world} GPU(s) (ShardedB200Ranker), thresholds {'shared over NVLink peer memory' if sharded.local.sharing else 'not shared'}, "
-                "one NCCL all-gather + certifying merge" if n_ugroups == 1 else
+                "NCCL all-to-all by user slice + certifying merge of the slice + all-gather of the merged slices" if n_ugroups == 1 else
                 f"users sharded over {world} GPU(s), NCCL all-gather of the results" if n_ishards == 1 else
                 f"grid: {n_ishards} item shards x {n_ugroups} user groups, NCCL all-gather + merge per user group, all-gather of the results"
             ),
