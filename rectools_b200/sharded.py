@@ -2,8 +2,9 @@
 
 The reference is single-device.  Default = the north-star multi-GPU scheme (section 8e): the object
 catalogue is split into contiguous ranges, every rank scores ALL subjects against its range and keeps a local top-k
-with GLOBAL object ids, the ranks exchange `n_rows * k` (id, score) pairs with ONE all-gather of a packed buffer (NCCL
-over NVLink on GPUs) and every rank merges the `world * k` candidates per subject.  Exact local lists => exact global
+with GLOBAL object ids into ONE packed buffer, the ranks exchange the buffers by subject slice (all-to-all, NCCL over NVLink
+on GPUs), every rank merges the `world * k` candidates of ITS slice of the subjects and one all-gather hands the merged
+slices round.  Exact local lists => exact global
 top-k; ties resolve by (score desc, id asc) in the merge exactly as inside a shard.
 
 Threshold sharing (GPUs, k <= 24): a rank's K'-th best score of a subject is a lower bound of the global K'-th best, so
@@ -61,7 +62,7 @@ def merge_padded_numpy(ids: np.ndarray, scores: np.ndarray, counts: np.ndarray, 
 
 class Packed:
     """One rank's results of one call in ONE int32 buffer: [ids n*k | score bits n*k | counts n | bound bits n], so that the
-    exchange is a single all-gather.  The four views alias the buffer."""
+    exchange moves one buffer per rank.  The four views alias the buffer."""
 
     def __init__(self, torch: tp.Any, n: int, k: int, device: tp.Any) -> None:
         self.n, self.k = n, k
