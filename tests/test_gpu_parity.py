@@ -13,7 +13,6 @@ from tests.helpers import (
     golden_keys,
     load_rank_case,
     parse_key,
-    ragged_to_padded,
     synth_factors,
     synth_viewed_csr,
 )

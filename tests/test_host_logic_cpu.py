@@ -2,7 +2,6 @@
 stand-in (no compute): argument validation in the reference's terms, which calls reach the library, and when the resident
 subject factors are (re-)uploaded for rankers that share one cached engine."""
 import ctypes as C
-import types
 
 import numpy as np
 import pytest

@@ -1,8 +1,5 @@
 """CPU: `install()` / `uninstall()` rebind the ranker name that VectorModel / EASEModel use (vector.py:28, ease.py:31).
 Needs the reference package: the checkout (build container) or its staged copy oracle/_ref."""
-import os
-import sys
-
 import pytest
 
 from oracle import stage_reference

@@ -2,7 +2,6 @@
 `ModelBase.recommend` (rectools/models/base.py:385-519).  The reference runs here through `oracle/implicit_stub`; the
 B200 ranker is replaced by the oracle-backed stand-in (`tests/helpers.OracleRanker`), so only the host logic is compared.
 Needs the reference package: the checkout (build container) or its staged copy oracle/_ref (GPU box)."""
-import os
 import sys
 
 import numpy as np

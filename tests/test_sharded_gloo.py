@@ -128,3 +128,41 @@ def test_shard_helpers():
     assert shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
     np.testing.assert_array_equal(split_whitelist([1, 3, 5, 7, 9], 3, 8), [0, 2, 4])
     assert len(split_whitelist([1, 2], 5, 9)) == 0
+
+
+def _worker_tiny(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        u, i = synth_factors(9, 50, 8, seed=2)
+        results = {}
+        ranker = ShardedB200Ranker("dot", u, i, local_factory=OracleShard)
+        for n in (1, 2, 5, 9):  # fewer rows than ranks, rows not divisible by the ranks: padded slices of the all-to-all
+            res = ranker.rank(np.arange(n), 4)
+            results[n] = [np.asarray(x) for x in res]
+        if rank == 0:
+            out.put(results)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slice_exchange_with_tiny_and_ragged_batches():
+    from oracle.topk_oracle import rank_oracle
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_tiny, args=(r, 4, port, out)) for r in range(4)]
+    for p in procs:
+        p.start()
+    results = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    u, i = synth_factors(9, 50, 8, seed=2)
+    for n, (s, ids, sc) in results.items():
+        es, eid, esc = rank_oracle("dot", u, i, np.arange(n), 4, accum="f64")
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(ids, eid, err_msg=f"n={n}")
+        np.testing.assert_allclose(sc, esc, rtol=1e-6, atol=1e-7)
