@@ -72,6 +72,13 @@ def _rows_of(csr: tp.Any, user_ids: np.ndarray) -> tp.Any:
     return rows
 
 
+def _has_repeats(ids: np.ndarray) -> bool:
+    """Any id listed twice?  (Strictly ascending targets -- the usual "all users" call -- are decided by one linear pass.)"""
+    if len(ids) < 2 or bool((np.diff(ids) > 0).all()):
+        return False
+    return len(np.unique(ids)) != len(ids)
+
+
 def finalize_scores(ranker: tp.Any, subject_ids: np.ndarray, scores: np.ndarray) -> np.ndarray:
     """Distance post-scaling of `_process_implicit_scores` (rank_implicit.py:132-140) on the padded [n, k] array."""
     dist = _as_distance(ranker.distance)
@@ -151,7 +158,7 @@ def recommend(  # pylint: disable=too-many-locals
     hot, warm, cold = model._split_targets_by_hot_warm_cold(users, ds, "user")  # pylint: disable=protected-access
     hot, warm, cold = model._check_targets_are_valid(hot, warm, cold, "user", on_unsupported_targets)  # pylint: disable=protected-access
     hot = np.asarray(hot, dtype=np.int64)
-    if np.size(warm) > 0 or np.size(cold) > 0 or len(np.unique(hot)) != len(hot):
+    if np.size(warm) > 0 or np.size(cold) > 0 or _has_repeats(hot):
         # (repeated targets: the reference's rank column runs across the repeats, `groupby(user).cumcount()`, base.py:778-791)
         return delegate()
 
@@ -209,7 +216,7 @@ def recommend_to_items(  # pylint: disable=too-many-locals
     hot, warm, cold = model._split_targets_by_hot_warm_cold(target_items, ds, "item")  # pylint: disable=protected-access
     hot, warm, cold = model._check_targets_are_valid(hot, warm, cold, "item", on_unsupported_targets)  # pylint: disable=protected-access
     hot = np.asarray(hot, dtype=np.int64)
-    if np.size(warm) > 0 or np.size(cold) > 0 or len(np.unique(hot)) != len(hot):
+    if np.size(warm) > 0 or np.size(cold) > 0 or _has_repeats(hot):
         return delegate()  # (the reference groups the self-filter by target id: repeated targets share one group)
 
     requested_k = k + 1 if filter_itself else k  # base.py:603
