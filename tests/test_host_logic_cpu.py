@@ -118,3 +118,30 @@ def test_in_place_refit_is_detected(lib):
     c = a.copy()
     c[-1, -1] += 1
     assert content_hash(a) != content_hash(c)
+
+
+def test_whitelist_must_be_sorted_unique_and_in_range(lib):
+    """the kernels merge viewed ids against ascending whitelist positions -- an unsorted whitelist is refused."""
+    from rectools_b200 import B200Ranker
+
+    ranker = B200Ranker("dot", np.ones((5, 3), np.float32), np.ones((7, 3), np.float32))
+    ranker.rank([0], k=2, sorted_object_whitelist=np.array([1, 4, 6]))
+    for bad in ([4, 1, 6], [1, 1, 4]):
+        with pytest.raises(ValueError, match="sorted"):
+            ranker.rank([0], k=2, sorted_object_whitelist=np.array(bad))
+    for bad in ([1, 7], [-1, 2]):
+        with pytest.raises(IndexError):
+            ranker.rank([0], k=2, sorted_object_whitelist=np.array(bad))
+
+
+def test_sparse_subjects_stay_sparse(lib):
+    """EASE: CSR subject factors are never densified as a whole; the requested rows go to the library as CSR."""
+    from rectools_b200 import B200Ranker
+
+    x = sparse.random(50, 7, density=0.3, format="csr", dtype=np.float32, random_state=0)
+    ranker = B200Ranker("dot", x, np.ones((7, 7), np.float32))
+    assert [c[0] for c in lib.calls] == ["create"]  # no resident dense subjects
+    ranker.rank([3, 1], k=2)
+    assert lib.calls[-1][0] == "topk" and lib.calls[-1][2] == 2
+    with pytest.raises(ValueError):
+        B200Ranker("dot", sparse.csr_matrix((4, 6), dtype=np.float32), np.ones((7, 7), np.float32))

@@ -166,3 +166,24 @@ def test_slice_exchange_with_tiny_and_ragged_batches():
         np.testing.assert_array_equal(s, es)
         np.testing.assert_array_equal(ids, eid, err_msg=f"n={n}")
         np.testing.assert_allclose(sc, esc, rtol=1e-6, atol=1e-7)
+
+
+def test_sharded_argument_checks_single_process():
+    """the sharded ranker range-checks subject ids and the whitelist like `B200Ranker` does."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        u, i = synth_factors(6, 30, 4, seed=1)
+        ranker = ShardedB200Ranker("dot", u, i, local_factory=OracleShard)
+        with pytest.raises(IndexError):
+            ranker.rank([0, 6], 3)
+        with pytest.raises(ValueError, match="sorted"):
+            ranker.rank([0], 3, sorted_object_whitelist=np.array([5, 2]))
+        with pytest.raises(IndexError):
+            ranker.rank([0], 3, sorted_object_whitelist=np.array([2, 30]))
+        with pytest.raises(ValueError, match="filter_pairs_csr"):
+            ranker.rank([0, 1], 3, sparse.csr_matrix((3, 30), dtype=np.float32))
+        s, ids, sc = ranker.rank([2, 0], 3)
+        assert len(ids) == 6
+    finally:
+        dist.destroy_process_group()
