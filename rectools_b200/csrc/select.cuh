@@ -440,10 +440,36 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) rescore_select_kernel(const Se
     }
 }
 
-// Wide mode: one block of 128 threads per row; up to WIDE_MAX candidates are re-scored (thread = candidate), sorted by
-// (score desc, id asc) with a bitonic network in shared memory, and the best kp <= 128 written.
+// Wide mode: one block of 128 threads per row, up to WIDE_MAX candidates.  Two stages: the candidates are sorted by their
+// APPROXIMATE scores first; only those within 2 eps of the kp-th best approximate score can reach the exact top-kp (everything
+// below ranks under kp others, see rescore_select_kernel) and are re-scored (thread = candidate) -- ~110 of ~180 gathered rows
+// at k = 100 -- then sorted by (exact score desc, id asc) with the same bitonic network in shared memory.
 constexpr int WIDE_THREADS = 128;
 constexpr int WIDE_MAX = 512;
+
+// best-first bitonic sort of s_sc / s_id [0, n), n a power of two (all threads of the block)
+__device__ __forceinline__ void block_bitonic_sort(float* s_sc, int* s_id, int n, int tid) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += WIDE_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float a = s_sc[i], b = s_sc[ixj];
+                    const int ai = s_id[i], bi2 = s_id[ixj];
+                    const bool up = (i & k) == 0;  // this pair sorts best-first
+                    const bool swap = up ? ranks_before(b, bi2, a, ai) : ranks_before(a, ai, b, bi2);
+                    if (swap) {
+                        s_sc[i] = b;
+                        s_sc[ixj] = a;
+                        s_id[i] = bi2;
+                        s_id[ixj] = ai;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
 
 __global__ void __launch_bounds__(WIDE_THREADS) rescore_wide_kernel(const SelectParams p) {
     extern __shared__ float s_dyn[];  // [d] subject row
@@ -451,6 +477,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) rescore_wide_kernel(const Select
     __shared__ int s_id[WIDE_MAX];
     __shared__ int s_off[65];
     __shared__ double s_red[WIDE_THREADS / 32];
+    __shared__ int s_cnt[WIDE_THREADS / 32];
     __shared__ float s_thr;
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -498,20 +525,23 @@ __global__ void __launch_bounds__(WIDE_THREADS) rescore_wide_kernel(const Select
     __syncthreads();
     const int total = s_off[p.n_lists];
     const double unorm2 = s_red[0] + s_red[1] + s_red[2] + s_red[3];
-    for (int c = tid; c < WIDE_MAX; c += WIDE_THREADS) {
+    const int ex = (p.row_exp ? p.row_exp[sel] : 0) + p.obj_exp;
+    const double eps = (double)p.eps_rel * sqrt(unorm2) * (double)p.max_obj_norm;
+    int n = 2;
+    while (n < total) n <<= 1;
+    // ---- stage 1: candidates with their approximate scores, best first
+    int n_valid = 0;
+    for (int c = tid; c < n; c += WIDE_THREADS) {
         float s = -INFINITY;
         int id = B200_PAD_ID;
         if (c < total) {
             int list = 0;
             while (c >= s_off[list + 1]) ++list;
-            const int e = c - s_off[list];
-            id = p.in_ids[((int64_t)list * p.list_stride_rows + sel) * p.L + e];
+            const int64_t o = ((int64_t)list * p.list_stride_rows + sel) * p.L + (c - s_off[list]);
+            id = p.in_ids[o];
             if (id != B200_PAD_ID && id >= 0) {
-                s = exact_score(p, s_dyn, id);
-                if (!(s < bs || (s == bs && id > bi))) {
-                    s = -INFINITY;
-                    id = B200_PAD_ID;
-                }
+                s = p.in_scores[o];
+                ++n_valid;
             } else {
                 id = B200_PAD_ID;
             }
@@ -519,40 +549,55 @@ __global__ void __launch_bounds__(WIDE_THREADS) rescore_wide_kernel(const Select
         s_sc[c] = s;
         s_id[c] = id;
     }
-    __syncthreads();
-    // bitonic sort, best first (only as far as the candidates reach: n = next power of two >= total, >= 2)
-    int n = 2;
-    while (n < total) n <<= 1;
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n; i += WIDE_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const float a = s_sc[i], b = s_sc[ixj];
-                    const int ai = s_id[i], bi2 = s_id[ixj];
-                    const bool up = (i & k) == 0;  // this pair sorts best-first
-                    const bool swap = up ? ranks_before(b, bi2, a, ai) : ranks_before(a, ai, b, bi2);
-                    if (swap) {
-                        s_sc[i] = b;
-                        s_sc[ixj] = a;
-                        s_id[i] = bi2;
-                        s_id[ixj] = ai;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    // valid candidates sort before the (-inf, PAD) fillers
-    int n_valid = 0;
-    for (int i = tid; i < n; i += WIDE_THREADS) n_valid += s_id[i] != B200_PAD_ID ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(B200_FULL_MASK, n_valid, o);
-    __shared__ int s_cnt[WIDE_THREADS / 32];
     if (lane == 0) s_cnt[warp] = n_valid;
     __syncthreads();
     n_valid = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
-    const int n_out = min(n_valid, p.kp);
+    block_bitonic_sort(s_sc, s_id, n, tid);
+    // ---- the band: [0, m) = candidates that may still reach the exact top-kp (first pass only; later passes re-score all)
+    int m = n_valid;
+    if (p.k0 == 0 && n_valid > p.kp) {
+        const double cut = (double)s_sc[p.kp - 1] - 2.0 * ldexp(eps, ex) * (1.0 + 1e-6);
+        int below = 0;  // sorted: the candidates under the cut form a suffix of [0, n_valid)
+        for (int c = tid; c < n_valid; c += WIDE_THREADS) below += (double)s_sc[c] < cut ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(B200_FULL_MASK, below, o);
+        __syncthreads();  // (s_cnt is read above by every thread before it is rewritten)
+        if (lane == 0) s_cnt[warp] = below;
+        __syncthreads();
+        m = n_valid - (s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3]);
+    }
+    __syncthreads();
+    // ---- stage 2: exact scores of the band, everything else leaves the ranking
+    int n2 = 2;
+    while (n2 < m) n2 <<= 1;
+    for (int c = tid; c < n; c += WIDE_THREADS) {
+        float s = -INFINITY;
+        int id = B200_PAD_ID;
+        if (c < m) {
+            id = s_id[c];
+            s = exact_score(p, s_dyn, id);
+            if (!(s < bs || (s == bs && id > bi))) {  // (later passes: at or above the previous pass's last entry)
+                s = -INFINITY;
+                id = B200_PAD_ID;
+            }
+        }
+        s_sc[c] = s;
+        s_id[c] = id;
+    }
+    __syncthreads();
+    block_bitonic_sort(s_sc, s_id, n2, tid);
+    int n_rank = 0;  // candidates still in the ranking (valid ones sort before the (-inf, PAD) fillers)
+    for (int i = tid; i < n2; i += WIDE_THREADS) n_rank += s_id[i] != B200_PAD_ID ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_rank += __shfl_xor_sync(B200_FULL_MASK, n_rank, o);
+    __syncthreads();
+    if (lane == 0) s_cnt[warp] = n_rank;
+    __syncthreads();
+    n_rank = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+    if (p.k0 > 0) n_valid = n_rank;  // later passes: only what survived the bound counts
+    const int n_out = min(n_rank, p.kp);
     for (int i = tid; i < p.kp; i += WIDE_THREADS) {
         const bool w = i < n_out;
         p.out_ids[lrow * p.k_out + p.k0 + i] = w ? s_id[i] : -1;
@@ -562,11 +607,9 @@ __global__ void __launch_bounds__(WIDE_THREADS) rescore_wide_kernel(const Select
         p.out_counts[lrow] = p.k0 + n_out;
         const bool overflow = s_flag != 0;
         if (s_thr > -INFINITY || overflow) {
-            const int ex = (p.row_exp ? p.row_exp[sel] : 0) + p.obj_exp;
             const double thr = ldexp((double)s_thr, -ex);
-            const double eps = (double)p.eps_rel * sqrt(unorm2) * (double)p.max_obj_norm;
-            const float e_k = n_valid >= p.kp ? s_sc[p.kp - 1] : -INFINITY;
-            const bool ok = !overflow && n_valid >= p.kp && (double)e_k > thr + eps + 1.2e-7 * fabs((double)e_k);
+            const float e_k = n_rank >= p.kp ? s_sc[p.kp - 1] : -INFINITY;
+            const bool ok = !overflow && n_valid >= p.kp && n_rank >= p.kp && (double)e_k > thr + eps + 1.2e-7 * fabs((double)e_k);
             if (!ok) {
                 const int slot = atomicAdd(p.fb_count, 1);
                 p.fb_rows[slot] = (int32_t)(lrow + p.fb_row0);
