@@ -26,7 +26,7 @@ from .ranker import Distance, _as_distance
 USER_COL, ITEM_COL, SCORE_COL, RANK_COL = "user_id", "item_id", "score", "rank"  # rectools/columns.py:21-27
 TARGET_ITEM_COL = "target_item_id"  # rectools/columns.py:23
 
-_CSR_CACHE: "tp.Dict[int, tp.Tuple[tp.Any, tp.Any, tp.Any]]" = {}
+_CSR_CACHE: "tp.Dict[int, tp.Tuple[tp.Any, tp.Any, tp.Any, tp.Optional[int]]]" = {}
 
 
 def viewed_csr(dataset: tp.Any) -> tp.Any:
@@ -34,6 +34,11 @@ def viewed_csr(dataset: tp.Any) -> tp.Any:
 
     The reference rebuilds this CSR from the interactions DataFrame on every `recommend()` call; it only depends on that
     (immutable by convention) table, so it is cached by the table's identity and dropped when the table is collected."""
+    return _viewed_entry(dataset)[0]
+
+
+def _viewed_entry(dataset: tp.Any) -> tp.Tuple[tp.Any, tp.Optional[int]]:
+    """(the cached CSR, `dataset.n_hot_users` of the same stamped table or None when the table cannot be stamped)."""
     from .integration import content_hash
 
     df = dataset.interactions.df
@@ -46,16 +51,30 @@ def viewed_csr(dataset: tp.Any) -> tp.Any:
         stamp = None
     hit = _CSR_CACHE.get(key)
     if hit is not None and hit[0]() is df and hit[2] == stamp:
-        return hit[1]
+        return hit[1], hit[3]
     csr = dataset.get_user_item_matrix(include_weights=False)
     if not csr.has_sorted_indices:
         csr.sort_indices()
+    # `Dataset.n_hot_users` (dataset.py:176-184) is a max over the user column on every access (0.06 s per 10^8 rows): the
+    # stamp above covers that column, so the value is kept with the CSR
+    n_hot = int(np.asarray(df[USER_COL].values).max()) + 1 if stamp is not None and len(df) > 0 else None
     try:
         ref = weakref.ref(df, lambda _r, key=key: _CSR_CACHE.pop(key, None))
     except TypeError:  # not weak-referenceable: do not cache
-        return csr
-    _CSR_CACHE[key] = (ref, csr, stamp)
-    return csr
+        return csr, n_hot
+    _CSR_CACHE[key] = (ref, csr, stamp, n_hot)
+    return csr, n_hot
+
+
+class _KnownHotUsers:  # pylint: disable=too-few-public-methods
+    """The dataset, with `n_hot_users` answered from the stamped cache entry instead of a scan of the interactions."""
+
+    def __init__(self, dataset: tp.Any, n_hot_users: int) -> None:
+        self._dataset = dataset
+        self.n_hot_users = n_hot_users
+
+    def __getattr__(self, name: str) -> tp.Any:
+        return getattr(self._dataset, name)
 
 
 def clear_viewed_cache() -> None:
@@ -70,6 +89,67 @@ def _rows_of(csr: tp.Any, user_ids: np.ndarray) -> tp.Any:
     rows = csr[user_ids]
     rows.has_sorted_indices = True  # row selection keeps the (sorted) order inside every row: spare the ranker an O(nnz) check
     return rows
+
+
+_PAR_MIN = 1 << 20  # output elements below which the table columns are written by the calling thread alone
+_PAR_POOL: tp.Optional[tp.Any] = None
+
+
+def _row_blocks(n_rows: int, work: tp.Callable[[int, int], None]) -> None:
+    """`work(r0, r1)` over blocks of rows on a small thread pool (numpy copies and gathers release the GIL; at 10^7 output
+    rows the single-threaded column writes cost as much as a quarter of the GPU pass)."""
+    global _PAR_POOL  # pylint: disable=global-statement
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    n_tasks = min(16, os.cpu_count() or 1)
+    if _PAR_POOL is None:
+        _PAR_POOL = ThreadPoolExecutor(max_workers=n_tasks, thread_name_prefix="b200table")
+    step = -(-n_rows // n_tasks)
+    list(_PAR_POOL.map(lambda i: work(i * step, min(n_rows, (i + 1) * step)), range(-(-n_rows // step))))
+
+
+def external_ids_of(table: np.ndarray, ids: np.ndarray, dtype: tp.Any) -> np.ndarray:
+    """`table[max(ids, 0)]` as `dtype` for a padded [n, k] id array (slots beyond a row's count hold -1 and are masked out
+    later): internal -> external ids by array indexing (`IdMap.external_ids` is sorted by internal id, identifiers.py:124-126)."""
+    table = np.asarray(table)
+    if ids.size < _PAR_MIN or ids.ndim != 2 or table.dtype.hasobject or len(table) == 0:
+        return np.asarray(table[np.maximum(ids, 0)], dtype=dtype)
+    out = np.empty(ids.shape, dtype=table.dtype)
+
+    def work(r0: int, r1: int) -> None:
+        np.take(table, ids[r0:r1], mode="clip", out=out[r0:r1])  # clip: -1 -> 0, as the maximum above
+
+    _row_blocks(ids.shape[0], work)
+    return np.asarray(out, dtype=dtype)
+
+
+def _repeat_rows(values: np.ndarray, k: int) -> np.ndarray:
+    """`np.repeat(values, k)` / (values [k], tiled per row when `values` is the row pattern) written by row blocks."""
+    n = len(values)
+    if n * k < _PAR_MIN or values.dtype.hasobject:
+        return np.repeat(values, k)
+    out = np.empty((n, k), dtype=values.dtype)
+
+    def work(r0: int, r1: int) -> None:
+        out[r0:r1] = values[r0:r1, None]
+
+    _row_blocks(n, work)
+    return out.reshape(-1)
+
+
+def _tile_rows(pattern: np.ndarray, n: int) -> np.ndarray:
+    """`np.tile(pattern, n)` written by row blocks."""
+    k = len(pattern)
+    if n * k < _PAR_MIN:
+        return np.tile(pattern, n)
+    out = np.empty((n, k), dtype=pattern.dtype)
+
+    def work(r0: int, r1: int) -> None:
+        out[r0:r1] = pattern[None, :]
+
+    _row_blocks(n, work)
+    return out.reshape(-1)
 
 
 def _has_repeats(ids: np.ndarray) -> bool:
@@ -109,8 +189,8 @@ def reco_table(
         targets, items, sc = target_ext[:0], item_ext.reshape(-1)[:0], scores.reshape(-1)[:0]
         ranks = np.empty(0, dtype=np.int64)
     elif full:
-        targets, items, sc = np.repeat(target_ext, k_out), item_ext.reshape(-1), scores.reshape(-1)
-        ranks = np.tile(np.arange(1, k_out + 1, dtype=np.int64), len(counts))
+        targets, items, sc = _repeat_rows(target_ext, k_out), item_ext.reshape(-1), scores.reshape(-1)
+        ranks = _tile_rows(np.arange(1, k_out + 1, dtype=np.int64), len(counts)) if add_rank_col else None
     else:
         mask = keep if keep is not None else np.arange(k_out, dtype=np.int32)[None, :] < counts[:, None]
         per_row = mask.sum(axis=1)
@@ -155,14 +235,16 @@ def recommend(  # pylint: disable=too-many-locals
     item_type = dataset.item_id_map.external_dtype
     ds = model._custom_transform_dataset_u2i(dataset, users, on_unsupported_targets, None)  # pylint: disable=protected-access
     whitelist = model._get_sorted_item_ids_to_recommend(items_to_recommend, ds)  # pylint: disable=protected-access
-    hot, warm, cold = model._split_targets_by_hot_warm_cold(users, ds, "user")  # pylint: disable=protected-access
+    csr_all, n_hot = _viewed_entry(ds) if filter_viewed else (None, None)
+    split_ds = ds if n_hot is None else _KnownHotUsers(ds, n_hot)
+    hot, warm, cold = model._split_targets_by_hot_warm_cold(users, split_ds, "user")  # pylint: disable=protected-access
     hot, warm, cold = model._check_targets_are_valid(hot, warm, cold, "user", on_unsupported_targets)  # pylint: disable=protected-access
     hot = np.asarray(hot, dtype=np.int64)
     if np.size(warm) > 0 or np.size(cold) > 0 or _has_repeats(hot):
         # (repeated targets: the reference's rank column runs across the repeats, `groupby(user).cumcount()`, base.py:778-791)
         return delegate()
 
-    csr = _rows_of(viewed_csr(ds), hot) if (filter_viewed and hot.size) else None
+    csr = _rows_of(csr_all, hot) if (filter_viewed and hot.size) else None
     user_vectors, item_vectors = model._get_u2i_vectors(ds)  # pylint: disable=protected-access
     if ranker_factory is None:
         from .integration import B200ImplicitRanker
@@ -177,10 +259,9 @@ def recommend(  # pylint: disable=too-many-locals
         scores = np.empty((0, 0), dtype=np.float32)
         counts = np.empty(0, dtype=np.int32)
     k_out = ids.shape[1]
-    # internal -> external ids by array indexing (`IdMap.external_ids` is sorted by internal id, identifiers.py:124-126);
     # unfilled slots (id -1, beyond `counts`) are masked out in reco_table
     user_ext = np.asarray(ds.user_id_map.external_ids[hot], dtype=user_type)
-    item_ext = np.asarray(ds.item_id_map.external_ids[np.maximum(ids, 0)], dtype=item_type)
+    item_ext = external_ids_of(ds.item_id_map.external_ids, ids, item_type)
     return reco_table(user_ext, item_ext, np.asarray(scores, dtype=np.float32), counts, k_out, add_rank_col)
 
 
@@ -237,6 +318,6 @@ def recommend_to_items(  # pylint: disable=too-many-locals
         keep &= ids != hot[:, None]
         keep &= np.cumsum(keep, axis=1) <= k  # the first k of what is left (groupby("tid").head(k))
     target_ext = np.asarray(ds.item_id_map.external_ids[hot], dtype=item_type)
-    item_ext = np.asarray(ds.item_id_map.external_ids[np.maximum(ids, 0)], dtype=item_type)
+    item_ext = external_ids_of(ds.item_id_map.external_ids, ids, item_type)
     return reco_table(target_ext, item_ext, np.asarray(scores, dtype=np.float32), keep.sum(axis=1), k_out, add_rank_col,
                       target_col=TARGET_ITEM_COL, keep=keep)

@@ -166,3 +166,60 @@ def test_viewed_csr_cache_notices_in_place_edits(fitted):
     finally:
         df.loc[df.index[0], "item_id"] = old
     assert (viewed_csr(dataset) != a).nnz == 0
+
+
+def test_warm_users_are_still_told_apart_with_the_cached_hot_count(fitted):
+    """`n_hot_users` is answered from the stamped CSR cache entry (not a scan of the table per call): a user known only from
+    the feature table is warm exactly as for the reference (base.py:676-700) -- refused, or dropped with a warning."""
+    import pandas as pd
+    from rectools.dataset import Dataset
+    from rectools.models import PureSVDModel
+
+    from rectools_b200.recommend import _viewed_entry, recommend
+    from tests.helpers import OracleRanker
+
+    _, _, df = fitted
+    users = np.unique(df["user_id"].values)
+    warm_id = int(users.max()) + 7
+    feats = pd.DataFrame({"id": np.append(users, warm_id), "feature": "f", "value": 1.0})
+    dataset = Dataset.construct(df, user_features_df=feats)
+    model = PureSVDModel(factors=8, random_state=0).fit(dataset)
+    assert dataset.user_id_map.size == len(users) + 1
+    assert _viewed_entry(dataset)[1] == dataset.n_hot_users == len(users)
+    ref = model.recommend(users[:50], dataset, k=5, filter_viewed=True)
+    _same(ref, recommend(model, users[:50], dataset, 5, True, ranker_factory=OracleRanker))
+    targets = np.append(users[:5], warm_id)
+    with pytest.raises(ValueError, match="warm"):
+        model.recommend(targets, dataset, k=5, filter_viewed=True)
+    with pytest.raises(ValueError, match="warm"):
+        recommend(model, targets, dataset, 5, True, ranker_factory=OracleRanker)
+    with pytest.warns(UserWarning):
+        ref = model.recommend(targets, dataset, k=5, filter_viewed=True, on_unsupported_targets="warn")
+    with pytest.warns(UserWarning):
+        got = recommend(model, targets, dataset, 5, True, on_unsupported_targets="warn", ranker_factory=OracleRanker)
+    _same(ref, got)
+    assert warm_id not in set(got["user_id"])
+
+
+def test_threaded_table_columns_match_reference(fitted, monkeypatch):
+    """Above 2^20 output rows the id gather / repeat / rank columns are written by row blocks on a thread pool: force that
+    path at test size and compare with the reference table (u2i with unfilled slots, u2i full, i2i)."""
+    import importlib
+
+    from tests.helpers import OracleRanker
+
+    rec = importlib.import_module("rectools_b200.recommend")  # (the package attribute of that name is the function)
+    monkeypatch.setattr(rec, "_PAR_MIN", 1)
+    model, dataset, _ = fitted
+    users = dataset.user_id_map.external_ids
+    for k, add_rank_col in ((7, True), (7, False), (dataset.item_id_map.size, True)):  # the last: ragged rows (-1 slots)
+        ref = model.recommend(users, dataset, k=k, filter_viewed=True, add_rank_col=add_rank_col)
+        _same(ref, rec.recommend(model, users, dataset, k, True, add_rank_col=add_rank_col, ranker_factory=OracleRanker))
+    items = dataset.item_id_map.external_ids[:40]
+    ref = model.recommend_to_items(items, dataset, k=6)
+    _same(ref, rec.recommend_to_items(model, items, dataset, 6, ranker_factory=OracleRanker))
+    table = np.arange(10, dtype=np.int64) * 3
+    ids = np.array([[1, -1], [9, 0]], dtype=np.int32)
+    assert rec.external_ids_of(table, ids, np.int64).tolist() == [[3, 0], [27, 0]]
+    assert rec._repeat_rows(np.array([5, 6, 7]), 2).tolist() == [5, 5, 6, 6, 7, 7]
+    assert rec._tile_rows(np.array([1, 2]), 3).tolist() == [1, 2, 1, 2, 1, 2]
